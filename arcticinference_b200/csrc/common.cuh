@@ -1,0 +1,136 @@
+// common.cuh - shared helpers for the sm_100a kernels of libarctic_b200.so
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/arctic_b200.h"
+
+namespace ab200 {
+
+// ---- error plumbing (thread-local last-error string, launch counter) ------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define AB200_REQUIRE(cond, code, ...)          \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::ab200::set_error(__VA_ARGS__);          \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define AB200_CUDA_OK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::ab200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                      \
+      return AB200_E_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// Checks the launch that was just enqueued (cudaPeekAtLastError does not clear sticky errors and
+// is legal during stream capture).
+#define AB200_CHECK_LAUNCH(name)                                                  \
+  do {                                                                            \
+    cudaError_t _e = cudaPeekAtLastError();                                       \
+    if (_e != cudaSuccess) {                                                      \
+      ::ab200::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+      (void)cudaGetLastError();                                                   \
+      return AB200_E_CUDA;                                                        \
+    }                                                                             \
+    ::ab200::count_launch();                                                      \
+  } while (0)
+
+inline int dtype_bytes(int32_t dt) { return dt == AB200_F32 ? 4 : 2; }
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- device helpers -------------------------------------------------------------------------
+// Storage-type traits: load/store/round through the tensor dtype.
+template <typename T> struct ST;
+template <> struct ST<float> {
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+  static __device__ __forceinline__ float round(float v) { return v; }
+};
+template <> struct ST<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float round(float v) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+  }
+};
+template <> struct ST<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ float round(float v) { return __half2float(__float2half_rn(v)); }
+};
+
+// 16-byte vector of storage elements
+template <typename T> struct Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+  union {
+    uint4 u;
+    T e[N];
+  };
+};
+
+__device__ __forceinline__ uint4 ld_stream_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum, result broadcast to every thread. `scratch` holds >= 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? scratch[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  float r = scratch[32];
+  __syncthreads();  // scratch may be reused immediately
+  return r;
+}
+
+// Packed (value, index) for a 64-bit max: larger logit wins; equal logits -> lower index wins.
+__device__ __forceinline__ uint32_t order_bits(float v) {
+  v = v + 0.0f;  // -0.0 -> +0.0 so that the two zeros tie (torch.argmax compares with >)
+  uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long pack_arg(float v, uint32_t idx) {
+  return (static_cast<unsigned long long>(order_bits(v)) << 32) |
+         static_cast<unsigned long long>(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ uint32_t unpack_idx(unsigned long long p) {
+  return 0xFFFFFFFFu - static_cast<uint32_t>(p & 0xFFFFFFFFull);
+}
+
+}  // namespace ab200

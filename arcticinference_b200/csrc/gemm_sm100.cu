@@ -1,0 +1,641 @@
+// gemm_sm100.cu - projection GEMMs of the Arctic LSTM speculator for sm_100a (hot path A).
+//
+//   out[M, N] = x[M, K] . w[N, K]^T        gate projection (arctic_speculator.py:555-561, 668)
+//   argmax_n ( x[M, K] . w[N, K]^T )       vocab head + greedy pick, logits never materialised
+//                                          (logits_processor_opt.py:83-107, arctic_speculator.py:726-732)
+//
+// Regime: M = draft batch (<= 128 per pass), N = 4D or the padded vocab, K = H or D.  The weight
+// matrix is streamed from HBM exactly once per call and dominates traffic (bytes = N*K*2), so the
+// kernel is a weight-streaming pipeline whose job is to keep HBM saturated:
+//   * warp 0  : TMA producer - cp.async.bulk.tensor 2D boxes (SWIZZLE_128B) of x [box_m x 64] and
+//               w [block_n x 64] into a multi-stage smem ring, mbarrier complete_tx signalling;
+//   * warp 1  : MMA issuer   - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//               (M=128, N=block_n, K=16; bf16 x bf16 -> fp32) with the accumulator in TMEM;
+//               tcgen05.commit releases smem stages / publishes the accumulator;
+//   * warps 2-5: epilogue    - tcgen05.ld 32x32b (lane = batch row, column = output feature), so
+//               the vocab arg-max is a thread-local scan; two TMEM accumulators let the epilogue
+//               of tile i overlap the main loop of tile i+1.
+//   * batch rows are the UMMA M dimension (lanes), features the N dimension: rows >= M are never
+//     fetched (TMA box covers box_m rows only) and cost no HBM traffic.
+//   * block_n is chosen per problem so that the tile count is a near multiple of the SM count
+//     (e.g. N = 16384 -> 147 tiles of 112 on 148 SMs).
+//   * bf16 results are rounded once from the fp32 accumulator, like the reference's cuBLAS GEMM;
+//     the arg-max compares the bf16-rounded logits and keeps the lowest index on ties
+//     (torch.argmax), across CTAs through a packed 64-bit atomicMax.
+//
+// The f32 parity mode (1e-5) uses a plain SIMT FFMA GEMM (exact fp32, no TF32) + row arg-max.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ab200 {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU - after ~2 s the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
+                                            int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, single CTA, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 weight-streaming GEMM
+// ------------------------------------------------------------------------------------------
+constexpr int kBlockK = 64;   // 64 bf16 = 128 B: one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kTileM = 128;   // UMMA M = TMEM lanes = batch rows per pass
+constexpr int kMaxBlockN = 256;
+constexpr int kGemmThreads = 192;
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB slot (only box_m rows are written)
+constexpr int kTmemCols = 512;                 // 2 accumulators x 256 columns
+constexpr int kMaxStages = 12;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // weights: streamed once
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // activations: re-read by every tile
+
+enum { EPI_STORE = 0, EPI_ARGMAX = 1 };
+
+struct GemmParams {
+  int32_t m_rows;       // valid rows in this pass (<= 128)
+  int32_t m0;           // first batch row of this pass
+  int32_t n_valid;      // columns that take part in the epilogue (N, or vocab for arg-max)
+  int32_t block_n;
+  int32_t num_n_tiles;
+  int32_t num_k_blocks;
+  int32_t stages;
+  uint32_t tx_bytes;    // bytes landing per stage
+  uint32_t idesc;
+  __nv_bfloat16* out;   // EPI_STORE
+  int64_t ldo;
+  unsigned long long* packed;  // EPI_ARGMAX, [M]
+};
+
+// K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);   // start address        bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                   // LBO (unused here)    bits [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;           // SBO = 1024 B         bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                   // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
+                   const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_kb = p.num_k_blocks;
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x) {
+        const int n0 = tile * p.block_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+          tma_load_2d(sa, &tmap_x, full_bar(stage), kb * kBlockK, p.m0, kEvictLast);
+          tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBlockK, n0, kEvictFirst);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kMaxBlockN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t da = smem_desc_sw128(sa);
+          const uint64_t db = smem_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                    // smem stage reusable once MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;     // batch row inside the pass
+    const bool row_ok = row < p.m_rows;
+    float best = -INFINITY;
+    uint32_t best_idx = 0xFFFFFFFFu;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int n0 = tile * p.block_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMaxBlockN;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if constexpr (EPI == EPI_STORE) {
+          if (row_ok && col0 < p.n_valid) {
+            __nv_bfloat16* dst = p.out + static_cast<int64_t>(p.m0 + row) * p.ldo + col0;
+            if (col0 + 16 <= p.n_valid) {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]),
+                                                         __uint_as_float(r[2 * j + 1]));
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+              for (int j = 0; j < 16 && col0 + j < p.n_valid; ++j)
+                dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          }
+        } else {
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              // the reference's GEMM returns bf16 logits: compare after rounding
+              const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j])));
+              const int col = col0 + j;
+              if (col < p.n_valid && v > best) {  // strict >: lowest index wins ties
+                best = v;
+                best_idx = static_cast<uint32_t>(col);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if constexpr (EPI == EPI_ARGMAX) {
+      if (row_ok && best_idx != 0xFFFFFFFFu) atomicMax(p.packed + p.m0 + row, pack_arg(best, best_idx));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, K] matrix (row stride ld), box = [box_rows x 64]
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld,
+                     int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  AB200_REQUIRE(enc != nullptr, AB200_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AB200_REQUIRE(r == CUDA_SUCCESS, AB200_E_CUDA,
+                "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld box_rows=%d", (int)r,
+                (long long)rows, (long long)K, (long long)ld, box_rows);
+  return AB200_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    (void)cudaGetLastError();
+  }
+  return n;
+}
+
+// Tile width: minimise waves * (block_n + fixed per-tile cost) so the tile count lands just under
+// a multiple of the SM count; ties go to the wider tile.
+int pick_block_n(int64_t N, int sms) {
+  int best_bn = 16;
+  double best_cost = 1e30;
+  for (int bn = 16; bn <= kMaxBlockN; bn += 16) {
+    const int64_t tiles = (N + bn - 1) / bn;
+    const int64_t waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 8.0);
+    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best_bn)) {
+      best_cost = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+template <int EPI>
+static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_rows, int64_t K,
+                            int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
+                            int64_t ldo, unsigned long long* packed, cudaStream_t s) {
+  AB200_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && aligned(x, 16) && aligned(w, 16),
+                AB200_E_INVALID,
+                "bf16 GEMM: K, ldx, ldw must be multiples of 8 and x/w 16-byte aligned");
+  AB200_REQUIRE(M > 0 && w_rows > 0 && K > 0 && n_valid > 0 && n_valid <= w_rows &&
+                    w_rows < (1LL << 31) && K < (1LL << 31),
+                AB200_E_INVALID, "bf16 GEMM: bad sizes");
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[EPI]) {
+    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_sm100<EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set[EPI] = true;
+  }
+  const int sms = sm_count();
+  const int bn = pick_block_n(n_valid, sms);
+  const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
+  const int box_m = static_cast<int>(((M < kTileM ? M : kTileM) + 7) / 8 * 8);
+  const uint32_t stage_bytes = kABytes + bn * 128;
+  int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
+
+  CUtensorMap tmx, tmw;
+  int rc = make_tmap(&tmx, x, M, K, ldx, box_m);
+  if (rc != AB200_OK) return rc;
+  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn);
+  if (rc != AB200_OK) return rc;
+
+  GemmParams p;
+  p.n_valid = static_cast<int32_t>(n_valid);
+  p.block_n = bn;
+  p.num_n_tiles = num_n_tiles;
+  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
+  p.stages = stages;
+  p.tx_bytes = static_cast<uint32_t>(box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
+  // instruction descriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+            (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.out = out;
+  p.ldo = ldo;
+  p.packed = packed;
+  const int grid = num_n_tiles < sms ? num_n_tiles : sms;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  for (int64_t m0 = 0; m0 < M; m0 += kTileM) {
+    p.m0 = static_cast<int32_t>(m0);
+    p.m_rows = static_cast<int32_t>(M - m0 < kTileM ? M - m0 : kTileM);
+    gemm_bf16_tn_sm100<EPI><<<grid, kGemmThreads, smem, s>>>(tmx, tmw, p);
+    AB200_CHECK_LAUNCH("gemm_bf16_tn_sm100");
+  }
+  return AB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact-fp32 SIMT GEMM (parity mode) : out[M,N] = x[M,K] . w[N,K]^T
+// ------------------------------------------------------------------------------------------
+constexpr int kSBM = 64, kSBN = 64, kSBK = 16;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+gemm_tn_simt(const TIn* __restrict__ x, const TIn* __restrict__ w, TOut* __restrict__ out, int M,
+             int N, int K, int64_t ldx, int64_t ldw, int64_t ldo) {
+  __shared__ float xs[kSBK][kSBM + 4];
+  __shared__ float wsm[kSBK][kSBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * kSBM, n0 = blockIdx.x * kSBN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += kSBK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;       // 0..1023
+      const int r = e >> 4, kk = e & 15; // row in tile, k in chunk
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+      xs[kk][r] = (gm < M && gk < K) ? ST<TIn>::to_f(x[gm * ldx + gk]) : 0.f;
+      wsm[kk][r] = (gn < N && gk < K) ? ST<TIn>::to_f(w[gn * ldw + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = xs[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = wsm[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) out[gm * ldo + gn] = ST<TOut>::from_f(acc[i][j]);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+static int launch_simt(const void* x, const void* w, void* out, int64_t M, int64_t N, int64_t K,
+                       int64_t ldx, int64_t ldw, int64_t ldo, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((N + kSBN - 1) / kSBN), static_cast<unsigned>((M + kSBM - 1) / kSBM));
+  gemm_tn_simt<TIn, TOut><<<grid, 256, 0, s>>>(static_cast<const TIn*>(x), static_cast<const TIn*>(w),
+                                               static_cast<TOut*>(out), (int)M, (int)N, (int)K, ldx,
+                                               ldw, ldo);
+  AB200_CHECK_LAUNCH("gemm_tn_simt");
+  return AB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// arg-max helpers
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const T* __restrict__ logits, int64_t N, int64_t ld,
+                   unsigned long long* __restrict__ packed) {
+  __shared__ unsigned long long sm[8];
+  const T* rowp = logits + blockIdx.x * ld;
+  float best = -INFINITY;
+  uint32_t bi = 0xFFFFFFFFu;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const float v = ST<T>::to_f(rowp[i]);
+    if (v > best) { best = v; bi = static_cast<uint32_t>(i); }
+  }
+  unsigned long long pk = bi == 0xFFFFFFFFu ? 0ull : pack_arg(best, bi);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, pk, o);
+    pk = other > pk ? other : pk;
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = pk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) pk = sm[i] > pk ? sm[i] : pk;
+    packed[blockIdx.x] = pk;
+  }
+}
+
+__global__ void argmax_unpack_kernel(const unsigned long long* __restrict__ packed,
+                                     int64_t* __restrict__ tokens, int64_t count, int64_t stride) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < count) tokens[i * stride] = static_cast<int64_t>(unpack_idx(packed[i]));
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" int32_t ab200_linear(const void* x, const void* w, void* out, int64_t M, int64_t N,
+                                int64_t K, int64_t ldx, int64_t ldw, int64_t ldo, int32_t dtype,
+                                void* stream) {
+  if (M == 0 || N == 0) return AB200_OK;
+  AB200_REQUIRE(x && w && out && M > 0 && N > 0 && K > 0, AB200_E_INVALID, "linear: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == AB200_F32) return launch_simt<float, float>(x, w, out, M, N, K, ldx, ldw, ldo, s);
+  AB200_REQUIRE(dtype == AB200_BF16, AB200_E_INVALID, "linear: dtype must be bf16 or f32");
+  AB200_REQUIRE(ldo % 8 == 0 && aligned(out, 16), AB200_E_INVALID,
+                "linear: ldo must be a multiple of 8 and out 16-byte aligned");
+  return launch_gemm_bf16<EPI_STORE>(x, w, M, N, K, ldx, ldw, N, static_cast<__nv_bfloat16*>(out), ldo,
+                                     nullptr, s);
+}
+
+extern "C" int32_t ab200_argmax_rows(const void* logits, int64_t M, int64_t N, int64_t ld,
+                                     int32_t dtype, uint64_t* packed_out, void* stream) {
+  if (M == 0) return AB200_OK;
+  AB200_REQUIRE(logits && packed_out && M > 0 && N > 0, AB200_E_INVALID, "argmax_rows: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto* pk = reinterpret_cast<unsigned long long*>(packed_out);
+  dim3 grid(static_cast<unsigned>(M));
+  if (dtype == AB200_F32)
+    argmax_rows_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(logits), N, ld, pk);
+  else if (dtype == AB200_BF16)
+    argmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), N, ld, pk);
+  else
+    AB200_REQUIRE(false, AB200_E_INVALID, "argmax_rows: dtype must be bf16 or f32");
+  AB200_CHECK_LAUNCH("argmax_rows_kernel");
+  return AB200_OK;
+}
+
+extern "C" int32_t ab200_head_argmax(const void* x, const void* w, int64_t M, int64_t w_rows,
+                                     int64_t K, int64_t vocab, int64_t ldx, int64_t ldw,
+                                     uint64_t* packed_out, int32_t dtype, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (M == 0) return AB200_OK;
+  AB200_REQUIRE(x && w && packed_out && M > 0 && K > 0 && vocab > 0 && vocab <= w_rows,
+                AB200_E_INVALID, "head_argmax: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == AB200_F32) {
+    const size_t need = static_cast<size_t>(M) * static_cast<size_t>(vocab) * sizeof(float);
+    AB200_REQUIRE(workspace && workspace_bytes >= need, AB200_E_WORKSPACE,
+                  "head_argmax(f32): workspace of %zu bytes required", need);
+    int rc = launch_simt<float, float>(x, w, workspace, M, vocab, K, ldx, ldw, vocab, s);
+    if (rc != AB200_OK) return rc;
+    return ab200_argmax_rows(workspace, M, vocab, vocab, AB200_F32, packed_out, stream);
+  }
+  AB200_REQUIRE(dtype == AB200_BF16, AB200_E_INVALID, "head_argmax: dtype must be bf16 or f32");
+  return launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0,
+                                      reinterpret_cast<unsigned long long*>(packed_out), s);
+}
+
+extern "C" int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
+                                       int64_t out_stride, void* stream) {
+  if (count == 0) return AB200_OK;
+  AB200_REQUIRE(packed && tokens_out && count > 0, AB200_E_INVALID, "argmax_unpack: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  argmax_unpack_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const unsigned long long*>(packed), tokens_out, count, out_stride);
+  AB200_CHECK_LAUNCH("argmax_unpack_kernel");
+  return AB200_OK;
+}
+
+// Tile width the tcgen05 GEMM would choose for N output features on `sms` SMs (bench reporting).
+extern "C" int32_t ab200_gemm_block_n(int64_t N, int32_t sms) {
+  return pick_block_n(N, sms > 0 ? sms : sm_count());
+}
+
+// bf16-input SIMT GEMM with fp32 accumulation, bf16 output: test/debug comparator for the tcgen05
+// kernel (not on the product path; exported for tests only).
+extern "C" int32_t ab200_linear_simt_bf16(const void* x, const void* w, void* out, int64_t M,
+                                          int64_t N, int64_t K, int64_t ldx, int64_t ldw,
+                                          int64_t ldo, void* stream) {
+  if (M == 0 || N == 0) return AB200_OK;
+  return launch_simt<__nv_bfloat16, __nv_bfloat16>(x, w, out, M, N, K, ldx, ldw, ldo,
+                                                    static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,300 @@
+// lstm_cell.cu - the Arctic LSTM speculator's fused elementwise work for sm_100a (hot path A):
+//   * rms_scale_kernel      : ln0(h) / sqrt(2)                 (arctic_speculator.py:88-91, 656-657)
+//   * sum_lstm_cell_kernel  : embedding gather + alpha-sum + 3 sigmoids + 2 RMS-LayerNorms with
+//                             affine + 2 erf-GELUs + LSTM gating  (arctic_speculator.py:667-689)
+// One CTA per batch row, 16-byte vector loads, values held in registers across the two row
+// reductions (warp-shuffle + one smem hop).  ~30 ATen launches of the reference become one.
+//
+// Rounding: with EMU (bf16/f16 storage) every value PyTorch eager would have materialised as a
+// tensor is rounded to the storage dtype at that point (the list is restated and
+// pinned in oracle/speculator_ref.py::emulated_cell).  The arithmetic between roundings follows
+// ATen's CUDA functors: fma for add-with-alpha, 1/(1+exp(-x)), x*0.5*(1+erf(x*M_SQRT1_2)),
+// mean = sum * (1/N), rsqrtf.
+//
+// Roofline: HBM bytes per row = e * D * (4 gates + 1 emb row + 1 c_prev + 2 outputs); at the
+// BASELINE batch sizes (64..512 rows) the kernel is launch-latency bound.
+#include "common.cuh"
+
+namespace ab200 {
+
+template <typename T, bool EMU>
+__device__ __forceinline__ float R(float v) {
+  if constexpr (EMU) return ST<T>::round(v);
+  else return v;
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <typename T, bool EMU, int ITEMS>
+__global__ void __launch_bounds__(1024)
+rms_scale_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t cols, int64_t ldx,
+                 int64_t ldy, float eps, float post_scale) {
+  constexpr int VN = Vec16<T>::N;
+  __shared__ float scratch[33];
+  const int64_t row = blockIdx.x;
+  const int nvec = cols / VN;
+  const T* xr = x + row * ldx;
+  T* yr = y + row * ldy;
+  float v[ITEMS][VN];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int vi = threadIdx.x + it * blockDim.x;
+    if (vi < nvec) {
+      Vec16<T> in;
+      in.u = *reinterpret_cast<const uint4*>(xr + vi * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        v[it][j] = ST<T>::to_f(in.e[j]);
+        ss += R<T, EMU>(v[it][j] * v[it][j]);
+      }
+    }
+  }
+  ss = block_sum(ss, scratch);
+  const float mean = R<T, EMU>(ss * (1.0f / static_cast<float>(cols)));
+  const float inv = R<T, EMU>(rsqrtf(R<T, EMU>(mean + eps)));
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int vi = threadIdx.x + it * blockDim.x;
+    if (vi < nvec) {
+      Vec16<T> out;
+#pragma unroll
+      for (int j = 0; j < VN; ++j)
+        out.e[j] = ST<T>::from_f(R<T, EMU>(v[it][j] * inv) * post_scale);
+      *reinterpret_cast<uint4*>(yr + vi * VN) = out.u;
+    }
+  }
+}
+
+template <typename T, bool EMU, int ITEMS>
+__global__ void __launch_bounds__(1024)
+sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restrict__ emb,
+                     const int64_t* __restrict__ tokens,
+                     const unsigned long long* __restrict__ packed,
+                     const T* cell_prev,  // may alias cell_out
+                     const T* __restrict__ wc, const T* __restrict__ bc,
+                     const T* __restrict__ ws, const T* __restrict__ bs,
+                     T* __restrict__ state_out, T* cell_out, int32_t D, int64_t vocab,
+                     float alpha, float eps) {
+  constexpr int VN = Vec16<T>::N;
+  __shared__ float scratch[33];
+  const int64_t row = blockIdx.x;
+  const int nvec = D / VN;
+
+  int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);  // never read outside the table
+
+  const T* g = gates + row * ldg;
+  const T* z = emb + tok * static_cast<int64_t>(D);
+  const float inv_d = 1.0f / static_cast<float>(D);
+
+  float f[ITEMS][VN], ig[ITEMS][VN], og[ITEMS][VN], cc[ITEMS][VN], c[ITEMS][VN];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int vi = threadIdx.x + it * blockDim.x;
+    if (vi < nvec) {
+      Vec16<T> gf, gi, go, gc, ze, cp;
+      gf.u = ld_stream_16(g + 0 * D + vi * VN);
+      gi.u = ld_stream_16(g + 1 * D + vi * VN);
+      go.u = ld_stream_16(g + 2 * D + vi * VN);
+      gc.u = ld_stream_16(g + 3 * D + vi * VN);
+      ze.u = *reinterpret_cast<const uint4*>(z + vi * VN);
+      if (cell_prev) cp.u = *reinterpret_cast<const uint4*>(cell_prev + row * D + vi * VN);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const float zz = ST<T>::to_f(ze.e[j]);
+        // torch.add(states, z.repeat(1,1,4), alpha): one rounding of fma(alpha, z, s)
+        f[it][j] = R<T, EMU>(sigmoid_f(R<T, EMU>(fmaf(alpha, zz, ST<T>::to_f(gf.e[j])))));
+        ig[it][j] = R<T, EMU>(sigmoid_f(R<T, EMU>(fmaf(alpha, zz, ST<T>::to_f(gi.e[j])))));
+        og[it][j] = R<T, EMU>(sigmoid_f(R<T, EMU>(fmaf(alpha, zz, ST<T>::to_f(go.e[j])))));
+        cc[it][j] = R<T, EMU>(fmaf(alpha, zz, ST<T>::to_f(gc.e[j])));
+        c[it][j] = cell_prev ? ST<T>::to_f(cp.e[j]) : 0.f;
+        ss += R<T, EMU>(cc[it][j] * cc[it][j]);
+      }
+    }
+  }
+  // cell_ln (RMS, affine) -> GELU -> * input gate ; c = c_prev * f + candidate
+  ss = block_sum(ss, scratch);
+  {
+    const float mean = R<T, EMU>(ss * inv_d);
+    const float inv = R<T, EMU>(rsqrtf(R<T, EMU>(mean + eps)));
+    ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (vi < nvec) {
+        Vec16<T> w, b;
+        w.u = *reinterpret_cast<const uint4*>(wc + vi * VN);
+        b.u = *reinterpret_cast<const uint4*>(bc + vi * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          float y = R<T, EMU>(cc[it][j] * inv);
+          y = R<T, EMU>(ST<T>::to_f(w.e[j]) * y);
+          y = R<T, EMU>(y + ST<T>::to_f(b.e[j]));
+          y = R<T, EMU>(gelu_erf_f(y));
+          y = R<T, EMU>(y * ig[it][j]);
+          float cn = R<T, EMU>(c[it][j] * f[it][j]);
+          cn = R<T, EMU>(cn + y);
+          c[it][j] = cn;
+          ss += R<T, EMU>(cn * cn);
+        }
+      }
+    }
+  }
+  // state_ln (RMS, affine) -> GELU -> * output gate
+  ss = block_sum(ss, scratch);
+  {
+    const float mean = R<T, EMU>(ss * inv_d);
+    const float inv = R<T, EMU>(rsqrtf(R<T, EMU>(mean + eps)));
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (vi < nvec) {
+        Vec16<T> w, b, so, co;
+        w.u = *reinterpret_cast<const uint4*>(ws + vi * VN);
+        b.u = *reinterpret_cast<const uint4*>(bs + vi * VN);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          float y = R<T, EMU>(c[it][j] * inv);
+          y = R<T, EMU>(ST<T>::to_f(w.e[j]) * y);
+          y = R<T, EMU>(y + ST<T>::to_f(b.e[j]));
+          y = R<T, EMU>(gelu_erf_f(y));
+          y = R<T, EMU>(y * og[it][j]);
+          so.e[j] = ST<T>::from_f(y);
+          co.e[j] = ST<T>::from_f(c[it][j]);
+        }
+        *reinterpret_cast<uint4*>(state_out + row * D + vi * VN) = so.u;
+        *reinterpret_cast<uint4*>(cell_out + row * D + vi * VN) = co.u;
+      }
+    }
+  }
+}
+
+// block size / items-per-thread for a row of `nvec` 16-byte vectors
+static bool row_launch_shape(int64_t nvec, int* threads, int* items) {
+  for (int it : {1, 2, 4}) {
+    int64_t t = (nvec + it - 1) / it;
+    t = (t + 31) / 32 * 32;
+    if (t <= 1024) {
+      *threads = static_cast<int>(t < 32 ? 32 : t);
+      *items = it;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <typename T, bool EMU>
+static int launch_rms(const void* x, void* y, int64_t rows, int64_t cols, int64_t ldx, int64_t ldy,
+                      float eps, float post_scale, cudaStream_t s) {
+  int threads, items;
+  AB200_REQUIRE(row_launch_shape(cols / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
+                "rms_scale: cols %lld too large", (long long)cols);
+  const T* xp = static_cast<const T*>(x);
+  T* yp = static_cast<T*>(y);
+  dim3 grid(static_cast<unsigned>(rows));
+  switch (items) {
+    case 1: rms_scale_kernel<T, EMU, 1><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
+    case 2: rms_scale_kernel<T, EMU, 2><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
+    default: rms_scale_kernel<T, EMU, 4><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
+  }
+  AB200_CHECK_LAUNCH("rms_scale_kernel");
+  return AB200_OK;
+}
+
+template <typename T, bool EMU>
+static int launch_cell(const void* gates, int64_t ldg, const void* emb, const int64_t* tokens,
+                       const uint64_t* packed, const void* cell_prev, const void* wc,
+                       const void* bc, const void* ws, const void* bs, void* state_out,
+                       void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
+                       cudaStream_t s) {
+  int threads, items;
+  AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
+                "sum_lstm_cell: D %lld too large", (long long)D);
+  dim3 grid(static_cast<unsigned>(B));
+#define AB200_CELL_ARGS                                                                        \
+  static_cast<const T*>(gates), ldg, static_cast<const T*>(emb), tokens,                       \
+      reinterpret_cast<const unsigned long long*>(packed), static_cast<const T*>(cell_prev),   \
+      static_cast<const T*>(wc), static_cast<const T*>(bc), static_cast<const T*>(ws),         \
+      static_cast<const T*>(bs), static_cast<T*>(state_out), static_cast<T*>(cell_out), (int)D, \
+      vocab, alpha, eps
+  switch (items) {
+    case 1: sum_lstm_cell_kernel<T, EMU, 1><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
+    case 2: sum_lstm_cell_kernel<T, EMU, 2><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
+    default: sum_lstm_cell_kernel<T, EMU, 4><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
+  }
+#undef AB200_CELL_ARGS
+  AB200_CHECK_LAUNCH("sum_lstm_cell_kernel");
+  return AB200_OK;
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t cols,
+                                   int64_t x_row_stride, int64_t y_row_stride, float eps,
+                                   float post_scale, int32_t dtype,
+                                   int32_t emulate_eager_rounding, void* stream) {
+  if (rows == 0) return AB200_OK;
+  AB200_REQUIRE(x && y && rows > 0 && cols > 0, AB200_E_INVALID, "rms_scale: bad arguments");
+  const int vn = 16 / dtype_bytes(dtype);
+  AB200_REQUIRE(cols % vn == 0 && x_row_stride % vn == 0 && y_row_stride % vn == 0 &&
+                    aligned(x, 16) && aligned(y, 16),
+                AB200_E_INVALID, "rms_scale: cols/strides must be multiples of %d elements and "
+                "pointers 16-byte aligned", vn);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool emu = emulate_eager_rounding != 0;
+  switch (dtype) {
+    case AB200_F32: return launch_rms<float, false>(x, y, rows, cols, x_row_stride, y_row_stride, eps, post_scale, s);
+    case AB200_BF16:
+      return emu ? launch_rms<__nv_bfloat16, true>(x, y, rows, cols, x_row_stride, y_row_stride, eps, post_scale, s)
+                 : launch_rms<__nv_bfloat16, false>(x, y, rows, cols, x_row_stride, y_row_stride, eps, post_scale, s);
+    case AB200_F16:
+      return emu ? launch_rms<__half, true>(x, y, rows, cols, x_row_stride, y_row_stride, eps, post_scale, s)
+                 : launch_rms<__half, false>(x, y, rows, cols, x_row_stride, y_row_stride, eps, post_scale, s);
+    default: AB200_REQUIRE(false, AB200_E_INVALID, "rms_scale: unsupported dtype %d", dtype);
+  }
+}
+
+extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
+                                       const void* emb_table, const int64_t* tokens,
+                                       const uint64_t* packed_argmax, const void* cell_prev,
+                                       const void* cell_ln_weight, const void* cell_ln_bias,
+                                       const void* state_ln_weight, const void* state_ln_bias,
+                                       void* state_out, void* cell_out, int64_t B, int64_t D,
+                                       int64_t vocab, float alpha, float eps, int32_t dtype,
+                                       int32_t emulate_eager_rounding, void* stream) {
+  if (B == 0) return AB200_OK;
+  AB200_REQUIRE(gates && emb_table && (tokens || packed_argmax) && cell_ln_weight &&
+                    cell_ln_bias && state_ln_weight && state_ln_bias && state_out && cell_out,
+                AB200_E_INVALID, "sum_lstm_cell: NULL pointer argument");
+  AB200_REQUIRE(B > 0 && D > 0 && vocab > 0, AB200_E_INVALID, "sum_lstm_cell: bad sizes");
+  const int vn = 16 / dtype_bytes(dtype);
+  AB200_REQUIRE(D % vn == 0 && gates_row_stride % vn == 0, AB200_E_INVALID,
+                "sum_lstm_cell: D and the gate row stride must be multiples of %d", vn);
+  AB200_REQUIRE(aligned(gates, 16) && aligned(emb_table, 16) && aligned(cell_ln_weight, 16) &&
+                    aligned(cell_ln_bias, 16) && aligned(state_ln_weight, 16) &&
+                    aligned(state_ln_bias, 16) && aligned(state_out, 16) && aligned(cell_out, 16) &&
+                    (!cell_prev || aligned(cell_prev, 16)),
+                AB200_E_INVALID, "sum_lstm_cell: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool emu = emulate_eager_rounding != 0;
+#define AB200_ARGS                                                                               \
+  gates, gates_row_stride, emb_table, tokens, packed_argmax, cell_prev, cell_ln_weight,          \
+      cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, s
+  switch (dtype) {
+    case AB200_F32: return launch_cell<float, false>(AB200_ARGS);
+    case AB200_BF16:
+      return emu ? launch_cell<__nv_bfloat16, true>(AB200_ARGS)
+                 : launch_cell<__nv_bfloat16, false>(AB200_ARGS);
+    case AB200_F16:
+      return emu ? launch_cell<__half, true>(AB200_ARGS) : launch_cell<__half, false>(AB200_ARGS);
+    default: AB200_REQUIRE(false, AB200_E_INVALID, "sum_lstm_cell: unsupported dtype %d", dtype);
+  }
+#undef AB200_ARGS
+}

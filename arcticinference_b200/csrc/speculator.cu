@@ -1,0 +1,141 @@
+// speculator.cu - library plumbing (error string, launch counter) and the whole-loop entry point
+// ab200_lstm_propose: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + arg-max) -> token unpack.
+// Replaces ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751): ~35 ATen
+// launches per step in the reference become 3 (plus ln0, one memset and one unpack per call),
+// all enqueued on one stream so the caller can capture the loop into a single CUDA graph.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ab200 {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+// tokens_out[b * S + s] = token of packed[s * B + b]
+__global__ void unpack_steps_kernel(const unsigned long long* __restrict__ packed,
+                                    int64_t* __restrict__ tokens_out, int64_t B, int32_t S) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < B * S) {
+    const int64_t s = i / B, b = i - s * B;
+    tokens_out[b * S + s] = static_cast<int64_t>(unpack_idx(packed[i]));
+  }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  size_t x0, gates, state[2], cell, packed, logits, total;
+};
+
+static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
+  const size_t e = dtype_bytes(sp->dtype);
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  w.x0 = take(static_cast<size_t>(B) * sp->input_hidden_dim * e);
+  w.gates = take(static_cast<size_t>(B) * 4 * sp->inner_dim * e);
+  w.state[0] = take(static_cast<size_t>(B) * sp->inner_dim * e);
+  w.state[1] = take(static_cast<size_t>(B) * sp->inner_dim * e);
+  w.cell = take(static_cast<size_t>(B) * sp->inner_dim * e);
+  w.packed = take(static_cast<size_t>(B) * S * sizeof(uint64_t));
+  w.logits = take(sp->dtype == AB200_F32 ? static_cast<size_t>(B) * sp->vocab * sizeof(float) : 0);
+  w.total = off;
+  return w;
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" const char* ab200_last_error(void) { return g_err; }
+extern "C" int32_t ab200_abi_version(void) { return 1; }
+extern "C" int64_t ab200_launch_count(void) { return g_launches; }
+
+extern "C" size_t ab200_lstm_workspace_bytes(const ab200_lstm_speculator* spec, int64_t B,
+                                             int32_t num_steps) {
+  if (!spec || B <= 0 || num_steps <= 0) return 0;
+  return plan(spec, B, num_steps).total;
+}
+
+extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int64_t* input_ids,
+                                      const void* hidden, int64_t ld_hidden, int64_t B,
+                                      int32_t num_steps, int64_t* tokens_out, void* states_out,
+                                      void* cells_out, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  AB200_REQUIRE(sp != nullptr, AB200_E_INVALID, "lstm_propose: NULL speculator descriptor");
+  if (B == 0 || num_steps == 0) return AB200_OK;
+  AB200_REQUIRE(B > 0 && num_steps > 0 && input_ids && hidden && tokens_out, AB200_E_INVALID,
+                "lstm_propose: bad arguments");
+  AB200_REQUIRE(sp->dtype == AB200_BF16 || sp->dtype == AB200_F32, AB200_E_INVALID,
+                "lstm_propose: dtype must be bf16 or f32");
+  AB200_REQUIRE(sp->forget_emb && sp->proj0 && sp->proj1 && sp->cell_ln_w && sp->cell_ln_b &&
+                    sp->state_ln_w && sp->state_ln_b && sp->head,
+                AB200_E_INVALID, "lstm_propose: NULL weight pointer");
+  AB200_REQUIRE(sp->vocab > 0 && sp->head_rows >= sp->vocab && sp->inner_dim > 0 &&
+                    sp->input_hidden_dim > 0,
+                AB200_E_INVALID, "lstm_propose: bad model dimensions");
+  const Workspace w = plan(sp, B, num_steps);
+  AB200_REQUIRE(workspace && workspace_bytes >= w.total && aligned(workspace, 256),
+                AB200_E_WORKSPACE, "lstm_propose: workspace of %zu bytes (256-byte aligned) required",
+                w.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const size_t e = dtype_bytes(sp->dtype);
+  const int64_t D = sp->inner_dim, H = sp->input_hidden_dim;
+  const size_t bd = static_cast<size_t>(B) * D * e;
+  uint64_t* packed = reinterpret_cast<uint64_t*>(ws + w.packed);
+
+  AB200_CUDA_OK(cudaMemsetAsync(packed, 0, static_cast<size_t>(B) * num_steps * sizeof(uint64_t), s));
+
+  const void* xin = hidden;
+  int64_t ldx = ld_hidden;
+  if (sp->scale_input) {
+    // ln0(h) / sqrt(2): ATen CUDA multiplies by the fp32 reciprocal of the scalar divisor
+    const float inv_sqrt2 = 1.0f / 1.41421356237309504880f;
+    int rc = ab200_rms_scale(hidden, ws + w.x0, B, H, ld_hidden, H, sp->eps, inv_sqrt2, sp->dtype,
+                             sp->emulate_eager_rounding, stream);
+    if (rc != AB200_OK) return rc;
+    xin = ws + w.x0;
+    ldx = H;
+  }
+  const void* cell_prev = nullptr;
+  for (int32_t step = 0; step < num_steps; ++step) {
+    const void* W = step == 0 ? sp->proj0 : sp->proj1;   // tie_weights: projs[min(step, 1)]
+    const int64_t K = step == 0 ? H : D;
+    int rc = ab200_linear(xin, W, ws + w.gates, B, 4 * D, K, ldx, K, 4 * D, sp->dtype, stream);
+    if (rc != AB200_OK) return rc;
+    void* state = states_out ? static_cast<char*>(states_out) + step * bd : ws + w.state[step & 1];
+    void* cell = cells_out ? static_cast<char*>(cells_out) + step * bd : ws + w.cell;
+    rc = ab200_sum_lstm_cell(ws + w.gates, 4 * D, sp->forget_emb, step == 0 ? input_ids : nullptr,
+                             step == 0 ? nullptr : packed + static_cast<size_t>(step - 1) * B,
+                             cell_prev, sp->cell_ln_w, sp->cell_ln_b, sp->state_ln_w, sp->state_ln_b,
+                             state, cell, B, D, sp->vocab, sp->alpha, sp->eps, sp->dtype,
+                             sp->emulate_eager_rounding, stream);
+    if (rc != AB200_OK) return rc;
+    rc = ab200_head_argmax(state, sp->head, B, sp->head_rows, D, sp->vocab, D, D,
+                           packed + static_cast<size_t>(step) * B, sp->dtype, ws + w.logits,
+                           w.total - w.logits, stream);
+    if (rc != AB200_OK) return rc;
+    xin = state;
+    ldx = D;
+    cell_prev = cell;
+  }
+  const int64_t n = B * num_steps;
+  unpack_steps_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const unsigned long long*>(packed), tokens_out, B, num_steps);
+  AB200_CHECK_LAUNCH("unpack_steps_kernel");
+  return AB200_OK;
+}

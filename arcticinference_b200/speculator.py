@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's ``ArcticLSTMSpeculator`` (hot path A boundary).
+
+The reference has no custom op for the draft head; its drop-in boundary is the
+Python method boundary of
+``arctic_inference/vllm/spec_dec/arctic_speculator.py::ArcticLSTMSpeculator``:
+
+* ``generate_proposals(input_ids[B], previous_hidden_states[B,H], num_predict_tokens) -> [B,S] int64``
+  (:753-866; ``ValueError`` when S > max_speculative_tokens, :759-762)
+* ``generate_states(last_tokens[B,1], previous_hidden_states[B,1,K], head_index, cell_states[B,1,D])
+  -> (state, cell)`` (:648-691)
+* ``generate_token_ids(batch_size, num_predict_tokens, last_tokens, previous_hidden_states,
+  next_tokens_tensors, cell_states)`` (:706-751)
+* parameter names/shapes as the reference loads them (:874-902): ``forget_emb.0.weight [V,D]``,
+  ``projs.0.weight [4D,H]``, ``projs.1.weight [4D,D]``, ``cell_ln.0.{weight,bias} [D]``,
+  ``state_ln.0.{weight,bias} [D]``, ``head.0.weight [V_pad64, D]``; ``load_weights`` fuses
+  ``forget/input/output/cell_proj`` in the gate order f, i, o, c.
+
+Everything numeric runs in libarctic_b200.so (hand-written sm_100a kernels) through the C ABI;
+PyTorch only owns device memory, the stream and the CUDA-graph capture.  There is no PyTorch or
+CPU fallback: without the native library construction raises.
+
+Only ``method="sum_lstm"`` with ``tie_weights`` / ``tie_lstm_embs`` (the configuration the
+reference's hot path asserts, :545, :663), TP = 1 and the unquantised head are built; the FP8
+``qhead`` (batch <= 32, :726-727) is out of scope (arithmetic lives in vllm 0.9.2).
+"""
+from __future__ import annotations
+
+import collections
+import ctypes
+import math
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+from . import _capi
+
+SQRT2 = 2 ** 0.5  # arctic_speculator.py:36
+
+
+def padding_size(size: int) -> int:
+    """arctic_speculator.py:39-44 - pad a batch to a multiple of pow2ceil(size)//4 so that few
+    CUDA graphs cover all batch sizes (1,2,3,4,6,8,12,16,24,32,48,64,96,128,...)."""
+    mult = (1 << (size - 1).bit_length()) // 4
+    if mult < 1:
+        return size
+    return (size + mult - 1) // mult * mult
+
+
+def pad_vocab_size(vocab_size: int, pad_to: int = 64) -> int:
+    """vocab_parallel_embedding.py pad_vocab_size (DEFAULT_VOCAB_PADDING_SIZE = 64)."""
+    return (vocab_size + pad_to - 1) // pad_to * pad_to
+
+
+class ArcticLSTMSpeculator:
+    """B200-native Arctic LSTM speculator draft head (see module docstring)."""
+
+    def __init__(self, *, vocab_size: int, input_hidden_dim: int, inner_dim: int, n_predict: int,
+                 num_lookahead_tokens: Optional[int] = None, max_num_seqs: int = 256,
+                 dtype: torch.dtype = torch.bfloat16, device: str | torch.device = "cuda",
+                 scale_input: bool = True, enforce_eager: bool = False,
+                 emulate_eager_rounding: bool = True, alpha_flavor: str = "cuda") -> None:
+        self._lib = _capi.lib()  # fail loudly if the native library is missing
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("dtype must be torch.bfloat16 or torch.float32")
+        if inner_dim % 8 or input_hidden_dim % 8:
+            raise ValueError("inner_dim and input_hidden_dim must be multiples of 8")
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.n_predict = n_predict
+        self.vocab_size = vocab_size
+        self.input_hidden_dim = input_hidden_dim
+        self.inner_dim = [inner_dim]
+        self.emb_dim = [inner_dim]
+        self.proj_dim = [inner_dim]
+        self.max_speculative_tokens = num_lookahead_tokens or n_predict
+        self.tie_weights = True
+        self.tie_lstm_embs = True
+        self.scale_input = scale_input
+        self.method = "sum_lstm"
+        self.emulate_eager_rounding = bool(emulate_eager_rounding) and dtype != torch.float32
+        # arctic_speculator.py:575-577
+        self.state_weight = 0.5 ** (0.5 / n_predict)
+        self.emb_weight = math.sqrt((1 - self.state_weight ** 2) * (inner_dim / 2))
+        alpha = torch.tensor(self.emb_weight / self.state_weight, dtype=torch.float32)
+        if alpha_flavor == "cpu" and dtype != torch.float32:
+            # ATen's CPU add kernel casts alpha to the tensor dtype; the CUDA kernel keeps fp32
+            alpha = alpha.to(dtype).to(torch.float32)
+        elif alpha_flavor not in ("cpu", "cuda"):
+            raise ValueError("alpha_flavor must be 'cuda' or 'cpu'")
+        self.alpha = float(alpha)
+        self.eps = 1e-6
+
+        D, H, V = inner_dim, input_hidden_dim, vocab_size
+        Vp = pad_vocab_size(V)
+        mk = lambda *shape: torch.zeros(*shape, dtype=dtype, device=self.device)
+        self._params: Dict[str, torch.Tensor] = collections.OrderedDict([
+            ("head.0.weight", mk(Vp, D)),
+            ("forget_emb.0.weight", mk(V, D)),
+            ("projs.0.weight", mk(4 * D, H)),
+            ("projs.1.weight", mk(4 * D, D)),
+            ("cell_ln.0.weight", mk(D)), ("cell_ln.0.bias", mk(D)),
+            ("state_ln.0.weight", mk(D)), ("state_ln.0.bias", mk(D)),
+        ])
+
+        # static buffers (arctic_speculator.py:590-610)
+        self.cuda_graph_max_batch_size = padding_size(max_num_seqs)
+        self.cuda_graph_mode = not enforce_eager
+        self.cuda_graphs: Dict[Tuple[int, int], torch.cuda.CUDAGraph] = {}
+        n = self.cuda_graph_max_batch_size
+        self.static_cuda_buffers = {
+            "last_tokens": torch.zeros(n, dtype=torch.long, device=self.device),
+            "previous_hidden_states": torch.zeros(n, H, dtype=dtype, device=self.device),
+            "next_tokens": torch.zeros(n, self.max_speculative_tokens, dtype=torch.long,
+                                       device=self.device),
+        }
+        self._workspace: Optional[torch.Tensor] = None
+        self._desc: Optional[_capi.LstmSpeculatorDesc] = None
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def named_parameters(self):
+        return list(self._params.items())
+
+    def _set_param(self, name: str, value: torch.Tensor) -> None:
+        p = self._params[name]
+        if tuple(p.shape) != tuple(value.shape):
+            if name.startswith("head") and value.shape[0] <= p.shape[0] and value.shape[1:] == p.shape[1:]:
+                p.zero_()                       # vocab-padding rows stay zero
+                p[:value.shape[0]].copy_(value)
+                return
+            raise ValueError(f"shape mismatch for {name}: {tuple(value.shape)} vs {tuple(p.shape)}")
+        p.copy_(value)
+
+    def load_weights(self, weights: Iterable[Tuple[str, torch.Tensor]]) -> None:
+        """arctic_speculator.py:874-902: drop the tied embeddings, fuse forget/input/output/cell
+        projections into ``projs.N.weight`` (order f, i, o, c), strip the ``speculator.`` prefix."""
+        weights = collections.OrderedDict((k.replace("speculator.", ""), v) for k, v in weights)
+        for tied in ("input_emb.0.weight", "cell_emb.0.weight", "output_emb.0.weight"):
+            weights.pop(tied, None)
+        for name in ("projs.0.weight", "projs.1.weight"):
+            parts = [name.replace("projs", p) for p in ("forget_proj", "input_proj", "output_proj", "cell_proj")]
+            if all(p in weights for p in parts):
+                weights[name] = torch.cat([weights.pop(p) for p in parts])
+        for name, w in weights.items():
+            if name.startswith("qhead"):
+                continue  # FP8 duplicate head: out of scope
+            if name in self._params:
+                self._set_param(name, w.to(device=self.device, dtype=self.dtype))
+        self._desc = None
+
+    # ---- native descriptor / workspace -------------------------------------------------------
+    def _descriptor(self) -> _capi.LstmSpeculatorDesc:
+        if self._desc is None:
+            p = self._params
+            d = _capi.LstmSpeculatorDesc()
+            d.dtype = _capi.torch_dtype_code(self.dtype)
+            d.emulate_eager_rounding = int(self.emulate_eager_rounding)
+            d.vocab = self.vocab_size
+            d.head_rows = p["head.0.weight"].shape[0]
+            d.input_hidden_dim = self.input_hidden_dim
+            d.inner_dim = self.inner_dim[0]
+            d.scale_input = int(self.scale_input)
+            d.alpha = self.alpha
+            d.eps = self.eps
+            d.forget_emb = p["forget_emb.0.weight"].data_ptr()
+            d.proj0 = p["projs.0.weight"].data_ptr()
+            d.proj1 = p["projs.1.weight"].data_ptr()
+            d.cell_ln_w = p["cell_ln.0.weight"].data_ptr()
+            d.cell_ln_b = p["cell_ln.0.bias"].data_ptr()
+            d.state_ln_w = p["state_ln.0.weight"].data_ptr()
+            d.state_ln_b = p["state_ln.0.bias"].data_ptr()
+            d.head = p["head.0.weight"].data_ptr()
+            self._desc = d
+        return self._desc
+
+    def _get_workspace(self, batch: int, steps: int) -> torch.Tensor:
+        need = self._lib.ab200_lstm_workspace_bytes(ctypes.byref(self._descriptor()), batch, steps)
+        if self._workspace is None or self._workspace.numel() < need:
+            if self.cuda_graphs:
+                raise RuntimeError("workspace would have to grow after CUDA graphs were captured")
+            biggest = self._lib.ab200_lstm_workspace_bytes(
+                ctypes.byref(self._descriptor()),
+                max(batch, self.cuda_graph_max_batch_size), max(steps, self.max_speculative_tokens))
+            self._workspace = torch.empty(max(need, biggest), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _propose_into(self, ids: torch.Tensor, hidden: torch.Tensor, out: torch.Tensor, batch: int,
+                      steps: int, states: Optional[torch.Tensor] = None,
+                      cells: Optional[torch.Tensor] = None) -> None:
+        ws = self._get_workspace(batch, steps)
+        with torch.cuda.device(self.device):
+            rc = self._lib.ab200_lstm_propose(
+                ctypes.byref(self._descriptor()), ids.data_ptr(), hidden.data_ptr(), hidden.stride(0),
+                batch, steps, out.data_ptr(),
+                states.data_ptr() if states is not None else None,
+                cells.data_ptr() if cells is not None else None,
+                ws.data_ptr(), ws.numel(), _capi.current_stream_ptr(self.device))
+        _capi.check(rc, "ab200_lstm_propose")
+
+    # ---- reference method boundary ------------------------------------------------------------
+    def generate_states(self, last_tokens: torch.Tensor, previous_hidden_states: torch.Tensor,
+                        head_index: int, cell_states: Optional[torch.Tensor] = None
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """arctic_speculator.py:648-691 - one step of ln0 (step 0) -> gate GEMM -> fused cell."""
+        lib, p = self._lib, self._params
+        B = last_tokens.shape[0]
+        D = self.inner_dim[0]
+        x = previous_hidden_states.reshape(B, -1)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        code = _capi.torch_dtype_code(self.dtype)
+        emu = int(self.emulate_eager_rounding)
+        stream = _capi.current_stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            if head_index == 0 and self.scale_input:                         # :656-657
+                y = torch.empty_like(x)
+                inv_sqrt2 = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(SQRT2, dtype=torch.float32))
+                _capi.check(lib.ab200_rms_scale(x.data_ptr(), y.data_ptr(), B, x.shape[1], x.stride(0),
+                                                y.stride(0), self.eps, inv_sqrt2, code, emu, stream),
+                            "ab200_rms_scale")
+                x = y
+            proj = p["projs.0.weight"] if head_index == 0 else p["projs.1.weight"]   # :659-660
+            if x.shape[1] != proj.shape[1]:
+                raise RuntimeError(f"hidden width {x.shape[1]} does not match projs weight {tuple(proj.shape)}")
+            gates = torch.empty(B, 4 * D, dtype=self.dtype, device=self.device)
+            _capi.check(lib.ab200_linear(x.data_ptr(), proj.data_ptr(), gates.data_ptr(), B, 4 * D,
+                                         x.shape[1], x.stride(0), proj.stride(0), gates.stride(0),
+                                         code, stream), "ab200_linear")
+            state = torch.empty(B, D, dtype=self.dtype, device=self.device)
+            cell = torch.empty(B, D, dtype=self.dtype, device=self.device)
+            toks = last_tokens.reshape(B).to(torch.long).contiguous()
+            cprev = None
+            if cell_states is not None:
+                cprev = cell_states.reshape(B, D).contiguous()
+            _capi.check(lib.ab200_sum_lstm_cell(
+                gates.data_ptr(), gates.stride(0), p["forget_emb.0.weight"].data_ptr(), toks.data_ptr(),
+                None, cprev.data_ptr() if cprev is not None else None,
+                p["cell_ln.0.weight"].data_ptr(), p["cell_ln.0.bias"].data_ptr(),
+                p["state_ln.0.weight"].data_ptr(), p["state_ln.0.bias"].data_ptr(),
+                state.data_ptr(), cell.data_ptr(), B, D, self.vocab_size, self.alpha, self.eps,
+                code, emu, stream), "ab200_sum_lstm_cell")
+        return state.unsqueeze(1), cell.unsqueeze(1)
+
+    def greedy_tokens(self, states: torch.Tensor) -> torch.Tensor:
+        """Head projection + arg-max for states [B, D] (logits_processor_opt.py:83-107,
+        arctic_speculator.py:726-732) -> [B] int64."""
+        lib, head = self._lib, self._params["head.0.weight"]
+        B, D = states.shape
+        states = states.contiguous()
+        packed = torch.zeros(B, dtype=torch.int64, device=self.device)
+        out = torch.empty(B, dtype=torch.long, device=self.device)
+        code = _capi.torch_dtype_code(self.dtype)
+        ws = None
+        if self.dtype == torch.float32:
+            ws = torch.empty(B * self.vocab_size, dtype=torch.float32, device=self.device)
+        stream = _capi.current_stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(lib.ab200_head_argmax(states.data_ptr(), head.data_ptr(), B, head.shape[0], D,
+                                              self.vocab_size, states.stride(0), head.stride(0),
+                                              packed.data_ptr(), code,
+                                              ws.data_ptr() if ws is not None else None,
+                                              ws.numel() * 4 if ws is not None else 0, stream),
+                        "ab200_head_argmax")
+            _capi.check(lib.ab200_argmax_unpack(packed.data_ptr(), out.data_ptr(), B, 1, stream),
+                        "ab200_argmax_unpack")
+        return out
+
+    def generate_token_ids(self, batch_size: int, num_predict_tokens: int, last_tokens: torch.Tensor,
+                           previous_hidden_states: torch.Tensor,
+                           next_tokens_tensors: List[Optional[torch.Tensor]],
+                           cell_states: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """arctic_speculator.py:706-751, step by step through the per-op entry points."""
+        for head_index in range(num_predict_tokens):
+            states, cell_states = self.generate_states(last_tokens, previous_hidden_states,
+                                                       head_index, cell_states)
+            previous_hidden_states = states
+            last_tokens = self.greedy_tokens(states.flatten(0, 1)).reshape(batch_size, -1)
+            if next_tokens_tensors[head_index] is None:
+                next_tokens_tensors[head_index] = last_tokens
+            else:
+                next_tokens_tensors[head_index].copy_(last_tokens)
+        return next_tokens_tensors
+
+    def generate_proposals(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor,
+                           num_predict_tokens: int) -> torch.Tensor:
+        """arctic_speculator.py:753-866: static buffers, batch padded to ``padding_size(B)``, one
+        CUDA graph per (padded batch, S) holding the whole S-step loop (3S+2 kernels + a memset)."""
+        if num_predict_tokens > self.max_speculative_tokens:
+            raise ValueError(f"Max speculative tokens for model is "
+                             f"{self.max_speculative_tokens}, but "
+                             f"{num_predict_tokens} were requested")
+        B = input_ids.size(0)
+        S = num_predict_tokens
+        if B == 0:
+            return torch.empty(0, S, dtype=torch.long, device=self.device)
+        if previous_hidden_states.shape != (B, self.input_hidden_dim):
+            raise RuntimeError(f"previous_hidden_states must be [{B}, {self.input_hidden_dim}]")
+        use_graph = self.cuda_graph_mode and B <= self.cuda_graph_max_batch_size
+        if not use_graph:
+            ids = input_ids.to(device=self.device, dtype=torch.long).contiguous()
+            hid = previous_hidden_states.to(device=self.device, dtype=self.dtype)
+            if hid.stride(1) != 1:
+                hid = hid.contiguous()
+            out = torch.empty(B, S, dtype=torch.long, device=self.device)
+            self._propose_into(ids, hid, out, B, S)
+            return out
+        bufs = self.static_cuda_buffers
+        bufs["last_tokens"][:B].copy_(input_ids)                       # :625
+        bufs["previous_hidden_states"][:B].copy_(previous_hidden_states)  # :629
+        padded = padding_size(B)                                       # :631
+        key = (padded, S)
+        g = self.cuda_graphs.get(key)
+        out_view = bufs["next_tokens"].view(-1)[:padded * S].view(padded, S)
+        if g is None:
+            self._get_workspace(self.cuda_graph_max_batch_size, self.max_speculative_tokens)
+            # warm-up on a side stream (first-use attribute setting must not happen in capture)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._propose_into(bufs["last_tokens"], bufs["previous_hidden_states"], out_view, padded, S)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._propose_into(bufs["last_tokens"], bufs["previous_hidden_states"], out_view, padded, S)
+            self.cuda_graphs[key] = g
+        g.replay()
+        return out_view[:B].clone()                                    # :862-866
+
+
+class ArcticProposer:
+    """Mirror of ``arctic_inference/vllm/spec_dec/arctic_proposer.py::ArcticProposer.propose``
+    (:149-166): host token ids -> device, ``generate_proposals``, device -> host numpy."""
+
+    def __init__(self, model: ArcticLSTMSpeculator) -> None:
+        self.model = model
+        self.device = model.device
+        self.input_hidden_dim = model.input_hidden_dim
+
+    def propose(self, context_token_ids, previous_hidden_states: torch.Tensor, num_predict_tokens: int):
+        assert num_predict_tokens > 0, \
+            f"num_predict_tokens must be greater than 0, got {num_predict_tokens}."
+        input_ids = torch.as_tensor(context_token_ids).to(self.device, non_blocking=True)
+        if previous_hidden_states.device != self.device:
+            previous_hidden_states = previous_hidden_states.to(self.device, non_blocking=True)
+        next_tokens = self.model.generate_proposals(
+            input_ids=input_ids,
+            previous_hidden_states=previous_hidden_states,
+            num_predict_tokens=num_predict_tokens,
+        )
+        return next_tokens.cpu().numpy()

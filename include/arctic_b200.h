@@ -1,0 +1,201 @@
+/* arctic_b200.h - C ABI of libarctic_b200.so: hand-written sm_100a kernels for ArcticInference's
+ * data-parallel hot path (Arctic LSTM speculator draft head + SwiftKV bulk KV write).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked "host".
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All entry
+ *     points only enqueue work on that stream: no allocation, no host<->device copy, no
+ *     synchronisation, so they can be captured into a CUDA graph.
+ *   - return value 0 = success, negative = error (AB200_E_*); the message of the last error on the
+ *     calling thread is returned by ab200_last_error().
+ *   - strides are in ELEMENTS of the tensor's dtype.
+ *   - the library contains no CPU fallback: without an sm_100 device every compute call fails.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * ArcticInference tree).
+ */
+#ifndef ARCTIC_B200_H_
+#define ARCTIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AB200_API __attribute__((visibility("default")))
+#else
+#define AB200_API
+#endif
+
+#define AB200_OK 0
+#define AB200_E_INVALID (-1)   /* bad argument (shape, alignment, dtype, NULL)        */
+#define AB200_E_UNSUPPORTED (-2) /* valid in the reference but not built here (e.g. fp8 KV) */
+#define AB200_E_CUDA (-3)      /* a CUDA runtime/driver call failed                    */
+#define AB200_E_WORKSPACE (-4) /* workspace too small                                  */
+
+enum ab200_dtype { AB200_F32 = 0, AB200_F16 = 1, AB200_BF16 = 2 };
+enum ab200_kv_cache_dtype { AB200_KV_AUTO = 0, AB200_KV_FP8_E4M3 = 1, AB200_KV_FP8_E5M2 = 2 };
+
+/* Message of the last error raised on this thread ("" if none). Never NULL. */
+AB200_API const char* ab200_last_error(void);
+/* ABI version (bumped on any signature change). */
+AB200_API int32_t ab200_abi_version(void);
+/* Number of kernel launches this library has enqueued on this thread since load (bench claim). */
+AB200_API int64_t ab200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path B: SwiftKV multi-layer bulk reshape-and-cache.
+ * Replaces: csrc/custom_ops/kernels.cu:86-155 (host launcher reshape_and_cache_flash_bulk) and
+ *           kernels.cu:12-69 (kernel), reached through torch op
+ *           arctic_inference::reshape_and_cache_flash_bulk (csrc/custom_ops/torch_bindings.cpp:5-19)
+ *           from arctic_inference/vllm/swiftkv/llama_swiftkv.py:623-628.
+ *
+ * For every token t < num_tokens with slot = slot_mapping[t] >= 0 and every layer l:
+ *   key_cache_l  [slot / block_size][slot % block_size][0 .. n) = keys  [t][l*n .. (l+1)*n)
+ *   value_cache_l[slot / block_size][slot % block_size][0 .. n) = values[t][l*n .. (l+1)*n)
+ * with n = num_heads * head_size; a cache block is `block_stride` elements apart (bs*n for vLLM's
+ * FlashAttention layout, 2*bs*n for FlashInfer's), dense [block_size, n] inside.  Bit-exact copy
+ * for kv_dtype AB200_KV_AUTO.  FP8 KV (dead code in the reference: ENABLE_FP8 is never defined,
+ * csrc/custom_ops/quant_utils.cuh:13,515-526) returns AB200_E_UNSUPPORTED.
+ *
+ * key_cache_ptrs / value_cache_ptrs: HOST arrays of num_layers device pointers.  They are passed
+ * to the kernel by value (no per-call H2D copy, unlike kernels.cu:135-146).
+ * k_scale_ptrs / v_scale_ptrs: HOST arrays of device float* (ignored for AUTO; may be NULL).
+ * num_layers == 0 or num_tokens == 0 is a successful no-op (kernels.cu:99-101).
+ */
+AB200_API int32_t ab200_kv_write_bulk(const void* keys, const void* values,
+                            int64_t key_row_stride, int64_t value_row_stride,
+                            void* const* key_cache_ptrs, void* const* value_cache_ptrs,
+                            const float* const* k_scale_ptrs, const float* const* v_scale_ptrs,
+                            int32_t num_layers,
+                            const int64_t* slot_mapping, int64_t num_tokens,
+                            int64_t block_stride, int32_t block_size,
+                            int32_t num_heads, int32_t head_size,
+                            int32_t src_dtype, int32_t kv_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path A: Arctic LSTM speculator draft head (method "sum_lstm").
+ * Replaces the eager-PyTorch op sequences inside
+ *   arctic_inference/vllm/spec_dec/arctic_speculator.py  (no custom op exists in the reference).
+ *
+ * `emulate_eager_rounding` (bf16/f16 only): round every intermediate to the storage dtype where
+ * PyTorch eager would have materialised a tensor (needed for >= 99.9 % draft-token agreement with
+ * the reference's bf16 path); 0 = keep fp32 inside the kernel and round once on output.
+ */
+
+/* y = x * rsqrt(mean(x^2, -1) + eps) * post_scale, row-wise.
+ * Replaces: MLPSpeculatorLayerNorm.forward without affine (arctic_speculator.py:88-91) followed
+ * by "/ SQRT2" (arctic_speculator.py:656-657; post_scale = 1/sqrt(2) in fp32). */
+AB200_API int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t cols,
+                        int64_t x_row_stride, int64_t y_row_stride,
+                        float eps, float post_scale, int32_t dtype,
+                        int32_t emulate_eager_rounding, void* stream);
+
+/* The fused sum + RMS-LayerNorm + LSTM-gate + GELU cell.
+ * Replaces: arctic_speculator.py:667-689 (embedding lookup, repeat(1,1,4), torch.add with alpha,
+ * split, sigmoid, cell_ln + GELU, input/forget gating, state_ln + GELU, output gate), ~30 ATen
+ * launches.
+ *   gates      [B, 4*D] gate pre-activations x @ W^T, order f | i | o | c  (row stride given)
+ *   emb_table  [vocab, D]
+ *   tokens     [B] int64 (used when packed_argmax == NULL)
+ *   packed_argmax [B] uint64 as written by ab200_head_argmax (token = 0xFFFFFFFF - low 32 bits);
+ *              when non-NULL it is the token source and `tokens` is ignored.
+ *   cell_prev  [B, D] or NULL (= zeros, the first step: arctic_speculator.py:781-785)
+ *   ln vectors [D]; outputs state_out, cell_out [B, D] (cell_out may alias cell_prev).
+ * D must be a multiple of 8 (16-byte vectors). */
+AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
+                            const void* emb_table, const int64_t* tokens,
+                            const uint64_t* packed_argmax,
+                            const void* cell_prev,
+                            const void* cell_ln_weight, const void* cell_ln_bias,
+                            const void* state_ln_weight, const void* state_ln_bias,
+                            void* state_out, void* cell_out,
+                            int64_t B, int64_t D, int64_t vocab,
+                            float alpha, float eps, int32_t dtype,
+                            int32_t emulate_eager_rounding, void* stream);
+
+/* out[M, N] = x[M, K] @ w[N, K]^T  (nn.Linear without bias).
+ * Replaces: self.projs[i](prev_state), arctic_speculator.py:555-561,668 (cuBLAS in the reference).
+ * bf16: TMA + tcgen05.mma (fp32 accumulation in TMEM), output rounded once to bf16.
+ * f32 : SIMT FFMA kernel (exact fp32, no TF32), the 1e-5 parity mode.
+ * bf16 requirements: K % 8 == 0, x and w 16-byte aligned, ldx % 8 == 0, ldw % 8 == 0. */
+AB200_API int32_t ab200_linear(const void* x, const void* w, void* out,
+                     int64_t M, int64_t N, int64_t K,
+                     int64_t ldx, int64_t ldw, int64_t ldo,
+                     int32_t dtype, void* stream);
+
+/* Fused vocabulary projection + greedy pick; logits are never written to memory (bf16).
+ * Replaces: LogitsProcessorOpt._get_logits (logits_processor_opt.py:83-107) ->
+ * UnquantizedEmbeddingMethod.apply (vocab_parallel_embedding.py:61-65) -> logits[..., :vocab] ->
+ * torch.argmax (arctic_speculator.py:726-732).
+ *   x [M, K], w [w_rows >= vocab, K] (vocab-padded head), only rows < vocab compete.
+ *   packed_out [M] uint64, MUST be zero on entry; on exit
+ *     packed = (order_preserving_bits(logit) << 32) | (0xFFFFFFFF - token)
+ *   so that a 64-bit max picks the largest logit and, on ties, the LOWEST token id (torch.argmax).
+ *   bf16: the logit is the fp32 accumulator rounded to bf16 (what the reference's GEMM returns).
+ *   f32 : needs workspace of M * vocab floats (logits are materialised), else AB200_E_WORKSPACE. */
+AB200_API int32_t ab200_head_argmax(const void* x, const void* w,
+                          int64_t M, int64_t w_rows, int64_t K, int64_t vocab,
+                          int64_t ldx, int64_t ldw,
+                          uint64_t* packed_out, int32_t dtype,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* tokens_out[i * out_stride] = 0xFFFFFFFF - low32(packed[i])  for i < count (int64 output). */
+AB200_API int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
+                            int64_t out_stride, void* stream);
+
+/* Row-wise argmax over materialised logits [M, N] (lowest index on ties) into the packed format.
+ * Used by the f32 path and by tests. packed_out need not be zeroed. */
+AB200_API int32_t ab200_argmax_rows(const void* logits, int64_t M, int64_t N, int64_t ld, int32_t dtype,
+                          uint64_t* packed_out, void* stream);
+
+/* Test / reporting hooks (not on the product path).
+ * ab200_linear_simt_bf16: bf16 inputs, fp32 FFMA accumulation, bf16 output - an independent
+ *   comparator for the tcgen05 kernel.
+ * ab200_gemm_block_n: tile width the tcgen05 GEMM picks for N output features on `sms` SMs
+ *   (sms <= 0: the current device). */
+AB200_API int32_t ab200_linear_simt_bf16(const void* x, const void* w, void* out,
+                               int64_t M, int64_t N, int64_t K,
+                               int64_t ldx, int64_t ldw, int64_t ldo, void* stream);
+AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
+
+/* Whole draft loop: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + argmax) -> token unpack.
+ * Replaces: ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751) as driven by
+ * generate_proposals (arctic_speculator.py:753-866), TP = 1, unquantised head.
+ * All launches go to `stream` (3*S + 3 kernels + 1 memset node), graph-capturable. */
+typedef struct ab200_lstm_speculator {
+  int32_t dtype;            /* AB200_BF16 or AB200_F32 */
+  int32_t emulate_eager_rounding;
+  int64_t vocab;            /* org vocab size (logits[..., :vocab]) */
+  int64_t head_rows;        /* rows of head weight (vocab padded to 64) */
+  int64_t input_hidden_dim; /* H */
+  int64_t inner_dim;        /* D = proj_dim = emb_dim = inner_dim */
+  int32_t scale_input;      /* apply ln0(h)/sqrt(2) before step 0 (arctic_speculator.py:656) */
+  float alpha;              /* emb_weight / state_weight (arctic_speculator.py:575-577,671) */
+  float eps;                /* 1e-6 (arctic_speculator.py:78) */
+  const void* forget_emb;   /* [vocab, D] */
+  const void* proj0;        /* [4D, H]  projs.0.weight */
+  const void* proj1;        /* [4D, D]  projs.1.weight */
+  const void* cell_ln_w; const void* cell_ln_b;   /* [D] */
+  const void* state_ln_w; const void* state_ln_b; /* [D] */
+  const void* head;         /* [head_rows, D] head.0.weight (tied across steps) */
+} ab200_lstm_speculator;
+
+AB200_API size_t ab200_lstm_workspace_bytes(const ab200_lstm_speculator* spec, int64_t B, int32_t num_steps);
+
+/* input_ids [B] int64, hidden [B, H] (row stride ld_hidden), tokens_out [B, num_steps] int64
+ * row-major.  If states_out / cells_out are non-NULL they receive the per-step hidden and cell
+ * states, [num_steps, B, D] (parity tests). */
+AB200_API int32_t ab200_lstm_propose(const ab200_lstm_speculator* spec,
+                           const int64_t* input_ids, const void* hidden, int64_t ld_hidden,
+                           int64_t B, int32_t num_steps, int64_t* tokens_out,
+                           void* states_out, void* cells_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCTIC_B200_H_ */
