@@ -72,9 +72,11 @@ def _reshape_and_cache_flash_bulk_cuda(keys: torch.Tensor, values: torch.Tensor,
         _check(keys.dtype == values.dtype == key_caches[0].dtype == value_caches[0].dtype,
                "keys/values/cache dtypes must match for kv_cache_dtype='auto'")
     _check(slot_mapping.dtype == torch.int64, "expected scalar type Long for slot_mapping")
+    num_tokens = slot_mapping.size(0)                                 # kernels.cu:108
+    if num_tokens == 0:
+        return
     _check(keys.dim() == 2 and values.dim() == 2 and keys.stride(1) == 1 and values.stride(1) == 1,
            "keys/values must be [num_tokens, num_layers*num_heads*head_size] with a dense last dim")
-    num_tokens = slot_mapping.size(0)                                 # kernels.cu:108
     _check(keys.size(0) >= num_tokens and values.size(0) >= num_tokens,
            "keys/values have fewer rows than slot_mapping")
     block_size = key_caches[0].size(1)                                # kernels.cu:109

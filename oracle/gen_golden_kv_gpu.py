@@ -23,7 +23,7 @@ from oracle import kv_write_ref as K  # noqa: E402
 CASES = {
     "flash_bf16": (4, 37, 2, 16, 16, np.uint16, torch.bfloat16, "flash", "perm", 0.1, 0, 0),
     "flashinfer_bf16": (3, 50, 4, 32, 8, np.uint16, torch.bfloat16, "flashinfer", "perm", 0.1, 0, 0),
-    "flash_fp16_seq": (2, 64, 8, 64, 16, np.uint16, torch.float16, "flash", "sequential", 0.0, 0, 0),
+    "flash_fp16_seq": (2, 40, 4, 32, 16, np.uint16, torch.float16, "flash", "sequential", 0.0, 0, 0),
     "flash_fp32": (2, 19, 2, 16, 16, np.uint32, torch.float32, "flash", "perm", 0.1, 0, 0),
     "strided_src_bf16": (3, 21, 2, 64, 16, np.uint16, torch.bfloat16, "flash", "perm", 0.05, 5, 24),
     "odd_n_bf16": (2, 13, 3, 20, 4, np.uint16, torch.bfloat16, "flashinfer", "perm", 0.0, 0, 0),

@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, exports every symbol include/arctic_b200.h
+declares, and the drop-in torch op is registered with the reference's schema (no compute here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from arcticinference_b200 import _build
+    return _build.build()
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "arctic_b200.h")).read()
+    return sorted(set(re.findall(r"AB200_API [\w\* ]+? (ab200_\w+)\(", text)))
+
+
+def test_header_declares_the_path():
+    syms = _header_symbols()
+    for required in ("ab200_kv_write_bulk", "ab200_sum_lstm_cell", "ab200_rms_scale", "ab200_linear",
+                     "ab200_head_argmax", "ab200_lstm_propose", "ab200_last_error"):
+        assert required in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    handle = ctypes.CDLL(built_lib)
+    for s in _header_symbols():
+        assert hasattr(handle, s), f"{s} declared in include/arctic_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(built_lib):
+    from arcticinference_b200 import _capi
+    assert sorted(_capi.SIGNATURES) == _header_symbols()
+    lib = _capi.lib()
+    assert lib.ab200_abi_version() == 1
+    assert lib.ab200_last_error() == b""
+
+
+def test_descriptor_struct_layout():
+    """ctypes mirror of struct ab200_lstm_speculator: 4+4+8*4+4+4+4(+4 pad)+8*8 bytes."""
+    from arcticinference_b200 import _capi
+    assert ctypes.sizeof(_capi.LstmSpeculatorDesc) == 120
+    assert _capi.LstmSpeculatorDesc.forget_emb.offset == 56
+
+
+def test_block_n_heuristic(built_lib):
+    from arcticinference_b200 import _capi
+    lib = _capi.lib()
+    # 16384 gate outputs on 148 SMs -> 147 tiles of 112; padded 128256 vocab -> 729 tiles of 176
+    assert lib.ab200_gemm_block_n(16384, 148) == 112
+    assert lib.ab200_gemm_block_n(128256, 148) == 176
+    for n in (16, 100, 1000, 4096, 201088):
+        bn = lib.ab200_gemm_block_n(n, 148)
+        assert bn % 16 == 0 and 16 <= bn <= 256
+
+
+def test_op_registered_with_reference_schema(built_lib):
+    from arcticinference_b200 import py_custom_ops
+    assert py_custom_ops.try_load_torch_library() is True
+    assert py_custom_ops.try_load_torch_library() is True  # idempotent
+    schema = str(torch.ops.arctic_inference.reshape_and_cache_flash_bulk.default._schema)
+    # csrc/custom_ops/torch_bindings.cpp:6-16
+    assert schema == ("arctic_inference::reshape_and_cache_flash_bulk(Tensor keys, Tensor values, "
+                      "Tensor(c!)[] key_caches, Tensor(d!)[] value_caches, Tensor slot_mapping, "
+                      "str kv_cache_dtype, Tensor(e)[] k_scales, Tensor(f)[] v_scales, "
+                      "int num_heads, int head_size) -> ()")
+
+
+def test_op_has_no_cpu_implementation(built_lib):
+    """torch_bindings.cpp:17-18 registers the CUDA key only; so do we - CPU tensors must not be
+    silently handled by a fallback."""
+    from arcticinference_b200 import py_custom_ops
+    py_custom_ops.try_load_torch_library()
+    k = torch.zeros(2, 32)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        py_custom_ops.reshape_and_cache_flash_bulk(k, k, [torch.zeros(1, 2, 32)], [torch.zeros(1, 2, 32)],
+                                                   torch.zeros(2, dtype=torch.long), "auto",
+                                                   [torch.ones(())], [torch.ones(())], 2, 16)
+
+
+def test_try_load_is_soft_when_library_missing(monkeypatch, built_lib):
+    """py_custom_ops.py:24-37: never raise, return False."""
+    from arcticinference_b200 import _capi, py_custom_ops
+    monkeypatch.setattr(py_custom_ops, "_registered", False)
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libarctic_b200.so")
+    assert py_custom_ops.try_load_torch_library() is False
+
+
+def test_speculator_fails_loudly_without_library(monkeypatch):
+    from arcticinference_b200 import _capi
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libarctic_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        ArcticLSTMSpeculator(vocab_size=64, input_hidden_dim=64, inner_dim=64, n_predict=3, device="cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "arcticinference_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_host_helpers():
+    from arcticinference_b200.speculator import padding_size, pad_vocab_size
+    assert [padding_size(n) for n in (1, 5, 9, 33, 64, 65, 257)] == [1, 6, 12, 48, 64, 96, 384]
+    assert pad_vocab_size(128256) == 128256 and pad_vocab_size(1000) == 1024
