@@ -44,14 +44,14 @@ SIGNATURES = {
     "ab200_sum_lstm_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_int32, c_int32,
-                                      c_void_p]),
+                                      c_void_p, c_void_p, c_void_p]),
     "ab200_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                c_int64, c_int64, c_int64, c_int32, c_void_p]),
     "ab200_linear_simt_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                          c_int64, c_int64, c_int64, c_void_p]),
     "ab200_head_argmax": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
-                                    c_int64, c_int64, c_void_p, c_int32, c_void_p, c_size_t,
-                                    c_void_p]),
+                                    c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_int32, c_void_p, c_size_t, c_void_p]),
     "ab200_argmax_unpack": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ab200_argmax_rows": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                     c_void_p]),

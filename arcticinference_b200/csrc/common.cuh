@@ -48,6 +48,28 @@ void count_launch(int n = 1);
     ::ab200::count_launch();                                                      \
   } while (0)
 
+// Programmatic dependent launch (PDL): kernels of one draft step are chained so that kernel N+1's
+// prologue (barrier init, TMEM allocation, weight prefetch) overlaps kernel N's tail.  Every
+// kernel calls pdl_launch_dependents() early and pdl_wait() before touching anything the previous
+// kernel produced; both are no-ops for launches without the attribute.  AB200_PDL=0 disables it.
+bool pdl_enabled();
+
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  }
+};
+
 inline int dtype_bytes(int32_t dt) { return dt == AB200_F32 ? 4 : 2; }
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -93,6 +115,11 @@ __device__ __forceinline__ void st_stream_16(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

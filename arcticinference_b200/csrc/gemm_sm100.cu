@@ -26,6 +26,8 @@
 // The f32 parity mode (1e-5) uses a plain SIMT FFMA GEMM (exact fp32, no TF32) + row arg-max.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ab200 {
@@ -79,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,31 +147,35 @@ __device__ __forceinline__ bool elect_one() {
 // ------------------------------------------------------------------------------------------
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B: one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kTileM = 128;   // UMMA M = TMEM lanes = batch rows per pass
+constexpr int kTileM = 128;   // UMMA M = TMEM lanes = batch rows per m-tile
 constexpr int kMaxBlockN = 256;
 constexpr int kGemmThreads = 192;
-constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB slot (only box_m rows are written)
-constexpr int kTmemCols = 512;                 // 2 accumulators x 256 columns
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB slot per m-tile (only box_m rows are written)
+constexpr int kTmemCols = 512;                 // 2 accumulator buffers x MT m-tiles x (256 / MT) columns
 constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxRowsPerPass = 512;           // MT <= 4 m-tiles share one weight stream
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // weights: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // activations: re-read by every tile
 
 enum { EPI_STORE = 0, EPI_ARGMAX = 1 };
 
 struct GemmParams {
-  int32_t m_rows;       // valid rows in this pass (<= 128)
-  int32_t m0;           // first batch row of this pass
+  int32_t m_rows;       // valid rows in this pass (<= MT * 128)
   int32_t n_valid;      // columns that take part in the epilogue (N, or vocab for arg-max)
   int32_t block_n;
   int32_t num_n_tiles;
   int32_t num_k_blocks;
   int32_t stages;
+  int32_t l2_prefetch_kb;  // extra W k-blocks prefetched into L2 before the dependency wait
   uint32_t tx_bytes;    // bytes landing per stage
   uint32_t idesc;
   __nv_bfloat16* out;   // EPI_STORE
   int64_t ldo;
-  unsigned long long* packed;  // EPI_ARGMAX, [M]
+  unsigned long long* packed;  // EPI_ARGMAX, [m_rows]
+  int64_t* tokens_out;         // EPI_ARGMAX, optional: written by the last CTA to finish
+  int64_t tokens_stride;
+  unsigned int* done_counter;  // EPI_ARGMAX, zero on entry (needed iff tokens_out)
 };
 
 // K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -177,23 +189,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-template <int EPI>
+// MT = number of 128-row m-tiles (batch rows up to MT*128) that share ONE pass over the weights.
+template <int EPI, int MT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  constexpr int kAccSlot = kMaxBlockN / MT;   // TMEM columns per (buffer, m-tile); block_n <= kAccSlot
+  constexpr uint32_t kASlot = MT * kABytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = kASlot + b_bytes;
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const uint32_t flag_slot = tmem_slot + 8u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -220,49 +236,78 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Programmatic dependent launch: let the next kernel in the stream start its own prologue now;
+  // it blocks in griddepcontrol.wait until this grid has completed and flushed.
+  pdl_launch_dependents();
+
   const int num_kb = p.num_k_blocks;
+  const int my_tiles = static_cast<int>(blockIdx.x) < p.num_n_tiles
+                           ? (p.num_n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x) {
-        const int n0 = tile * p.block_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-          tma_load_2d(sa, &tmap_x, full_bar(stage), kb * kBlockK, p.m0, kEvictLast);
-          tma_load_2d(sa + kABytes, &tmap_w, full_bar(stage), kb * kBlockK, n0, kEvictFirst);
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
-        }
+      const int total = my_tiles * num_kb;   // linearised (tile, k-block) sequence of this CTA
+      auto n0_of = [&](int g) { return (static_cast<int>(blockIdx.x) + (g / num_kb) * static_cast<int>(gridDim.x)) * p.block_n; };
+      auto load_x = [&](int g, int stage) {
+        const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+        for (int t = 0; t < MT; ++t)
+          tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK, t * kTileM, kEvictLast);
+      };
+      auto load_w = [&](int g, int stage) {
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK, n0_of(g), kEvictFirst);
+      };
+      // The weights do not depend on the previous kernel: fill the ring with W (and warm L2 with
+      // the k-blocks after that) BEFORE waiting for the producer of x.
+      const int pre = total < stages ? total : stages;
+      for (int g = 0; g < pre; ++g) {
+        mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
+        load_w(g, g);
+      }
+      const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
+      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kBlockK, n0_of(g));
+      pdl_wait();
+      for (int g = 0; g < pre; ++g) load_x(g, g);
+      int stage = pre == stages ? 0 : pre;
+      uint32_t phase = pre == stages ? 1u : 0u;
+      for (int g = pre; g < total; ++g) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+        load_x(g, stage);
+        load_w(g, stage);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    pdl_wait();
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * kMaxBlockN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = smem_desc_sw128(sa);
-          const uint64_t db = smem_desc_sw128(sa + kABytes);
+          const uint64_t db = smem_desc_sw128(sa + kASlot);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-            umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int t = 0; t < MT; ++t) {
+            const uint64_t da = smem_desc_sw128(sa + t * kABytes);
+            const uint32_t tmem_d = tmem_base + (acc * MT + t) * kAccSlot;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+              umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(empty_bar(stage));                    // smem stage reusable once MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+          umma_commit(empty_bar(stage));                      // smem stage reusable once MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulators complete
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -270,52 +315,58 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    pdl_wait();
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;     // batch row inside the pass
-    const bool row_ok = row < p.m_rows;
-    float best = -INFINITY;
-    uint32_t best_idx = 0xFFFFFFFFu;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_n_tiles; tile += gridDim.x, ++it) {
+    float best[MT];
+    uint32_t best_idx[MT];
+#pragma unroll
+    for (int t = 0; t < MT; ++t) { best[t] = -INFINITY; best_idx[t] = 0xFFFFFFFFu; }
+    for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int n0 = tile * p.block_n;
+      const int n0 = (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * p.block_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kMaxBlockN;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c0;
-        if constexpr (EPI == EPI_STORE) {
-          if (row_ok && col0 < p.n_valid) {
-            __nv_bfloat16* dst = p.out + static_cast<int64_t>(p.m0 + row) * p.ldo + col0;
-            if (col0 + 16 <= p.n_valid) {
-              uint32_t w[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]),
-                                                         __uint_as_float(r[2 * j + 1]));
-                w[j] = *reinterpret_cast<uint32_t*>(&h);
+      for (int t = 0; t < MT; ++t) {
+        const int row = t * kTileM + quad * 32 + lane;   // batch row inside the pass
+        const bool row_ok = row < p.m_rows;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * MT + t) * kAccSlot;
+        if (t * kTileM + quad * 32 >= p.m_rows) continue;  // whole warp out of range (warp-uniform)
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c0;
+          if constexpr (EPI == EPI_STORE) {
+            if (row_ok && col0 < p.n_valid) {
+              __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0;
+              if (col0 + 16 <= p.n_valid) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]),
+                                                           __uint_as_float(r[2 * j + 1]));
+                  w[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              } else {
+                for (int j = 0; j < 16 && col0 + j < p.n_valid; ++j)
+                  dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
               }
-              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-            } else {
-              for (int j = 0; j < 16 && col0 + j < p.n_valid; ++j)
-                dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
             }
-          }
-        } else {
-          if (row_ok) {
+          } else {
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              // the reference's GEMM returns bf16 logits: compare after rounding
-              const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j])));
-              const int col = col0 + j;
-              if (col < p.n_valid && v > best) {  // strict >: lowest index wins ties
-                best = v;
-                best_idx = static_cast<uint32_t>(col);
+              for (int j = 0; j < 16; ++j) {
+                // the reference's GEMM returns bf16 logits: compare after rounding
+                const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j])));
+                const int col = col0 + j;
+                if (col < p.n_valid && v > best[t]) {  // strict >: lowest index wins ties
+                  best[t] = v;
+                  best_idx[t] = static_cast<uint32_t>(col);
+                }
               }
             }
           }
@@ -326,7 +377,33 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
     if constexpr (EPI == EPI_ARGMAX) {
-      if (row_ok && best_idx != 0xFFFFFFFFu) atomicMax(p.packed + p.m0 + row, pack_arg(best, best_idx));
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const int row = t * kTileM + quad * 32 + lane;
+        if (row < p.m_rows && best_idx[t] != 0xFFFFFFFFu) atomicMax(p.packed + row, pack_arg(best[t], best_idx[t]));
+      }
+      if (p.tokens_out != nullptr) {
+        // The last CTA to finish turns the packed maxima into int64 token ids (folds the
+        // separate unpack launch).  128 epilogue threads, named barrier 1.
+        const int et = threadIdx.x - 64;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const unsigned int prev = atomicAdd(p.done_counter, 1u);
+          const uint32_t last = prev == gridDim.x - 1 ? 1u : 0u;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_slot), "r"(last) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t last;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag_slot) : "memory");
+        if (last) {
+          __threadfence();
+          for (int r = et; r < p.m_rows; r += 128) {
+            const unsigned long long pk = *reinterpret_cast<volatile unsigned long long*>(p.packed + r);
+            p.tokens_out[static_cast<int64_t>(r) * p.tokens_stride] = static_cast<int64_t>(unpack_idx(pk));
+          }
+        }
+      }
     }
   }
 
@@ -391,10 +468,10 @@ static int sm_count() {
 
 // Tile width: minimise waves * (block_n + fixed per-tile cost) so the tile count lands just under
 // a multiple of the SM count; ties go to the wider tile.
-int pick_block_n(int64_t N, int sms) {
+int pick_block_n(int64_t N, int sms, int max_bn) {
   int best_bn = 16;
   double best_cost = 1e30;
-  for (int bn = 16; bn <= kMaxBlockN; bn += 16) {
+  for (int bn = 16; bn <= max_bn; bn += 16) {
     const int64_t tiles = (N + bn - 1) / bn;
     const int64_t waves = (tiles + sms - 1) / sms;
     const double cost = static_cast<double>(waves) * (bn + 8.0);
@@ -406,57 +483,96 @@ int pick_block_n(int64_t N, int sms) {
   return best_bn;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+struct ArgmaxExtra {
+  unsigned long long* packed = nullptr;
+  int64_t* tokens_out = nullptr;
+  int64_t tokens_stride = 0;
+  unsigned int* done_counter = nullptr;
+};
+
+template <int EPI, int MT>
+static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
+                            int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
+                            int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_sm100<EPI, MT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  const int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
+  const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
+  const int box_m = MT == 1 ? static_cast<int>((m_rows + 7) / 8 * 8) : kTileM;
+  const uint32_t stage_bytes = MT * kABytes + bn * 128;
+  int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
+
+  CUtensorMap tmx, tmw;
+  int rc = make_tmap(&tmx, x, m_rows, K, ldx, box_m);
+  if (rc != AB200_OK) return rc;
+  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn);
+  if (rc != AB200_OK) return rc;
+
+  GemmParams p;
+  p.m_rows = static_cast<int32_t>(m_rows);
+  p.n_valid = static_cast<int32_t>(n_valid);
+  p.block_n = bn;
+  p.num_n_tiles = num_n_tiles;
+  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
+  p.stages = stages;
+  p.l2_prefetch_kb = pdl_enabled() ? env_int("AB200_L2_PREFETCH_KB", 0) : 0;
+  p.tx_bytes = static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
+  // instruction descriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+            (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.out = out;
+  p.ldo = ldo;
+  p.packed = ax.packed;
+  p.tokens_out = ax.tokens_out;
+  p.tokens_stride = ax.tokens_stride;
+  p.done_counter = ax.done_counter;
+  const int grid = num_n_tiles < sms ? num_n_tiles : sms;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  LaunchCfg cfg(dim3(grid), dim3(kGemmThreads), smem, s);
+  AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_bf16_tn_sm100<EPI, MT>, tmx, tmw, p));
+  AB200_CHECK_LAUNCH("gemm_bf16_tn_sm100");
+  return AB200_OK;
+}
+
 template <int EPI>
 static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
-                            int64_t ldo, unsigned long long* packed, cudaStream_t s) {
+                            int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
   AB200_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && aligned(x, 16) && aligned(w, 16),
                 AB200_E_INVALID,
                 "bf16 GEMM: K, ldx, ldw must be multiples of 8 and x/w 16-byte aligned");
   AB200_REQUIRE(M > 0 && w_rows > 0 && K > 0 && n_valid > 0 && n_valid <= w_rows &&
                     w_rows < (1LL << 31) && K < (1LL << 31),
                 AB200_E_INVALID, "bf16 GEMM: bad sizes");
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[EPI]) {
-    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_sm100<EPI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set[EPI] = true;
-  }
-  const int sms = sm_count();
-  const int bn = pick_block_n(n_valid, sms);
-  const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
-  const int box_m = static_cast<int>(((M < kTileM ? M : kTileM) + 7) / 8 * 8);
-  const uint32_t stage_bytes = kABytes + bn * 128;
-  int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
-
-  CUtensorMap tmx, tmw;
-  int rc = make_tmap(&tmx, x, M, K, ldx, box_m);
-  if (rc != AB200_OK) return rc;
-  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn);
-  if (rc != AB200_OK) return rc;
-
-  GemmParams p;
-  p.n_valid = static_cast<int32_t>(n_valid);
-  p.block_n = bn;
-  p.num_n_tiles = num_n_tiles;
-  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
-  p.stages = stages;
-  p.tx_bytes = static_cast<uint32_t>(box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
-  // instruction descriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
-            (static_cast<uint32_t>(kTileM >> 4) << 24);
-  p.out = out;
-  p.ldo = ldo;
-  p.packed = packed;
-  const int grid = num_n_tiles < sms ? num_n_tiles : sms;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
-  for (int64_t m0 = 0; m0 < M; m0 += kTileM) {
-    p.m0 = static_cast<int32_t>(m0);
-    p.m_rows = static_cast<int32_t>(M - m0 < kTileM ? M - m0 : kTileM);
-    gemm_bf16_tn_sm100<EPI><<<grid, kGemmThreads, smem, s>>>(tmx, tmw, p);
-    AB200_CHECK_LAUNCH("gemm_bf16_tn_sm100");
+  AB200_REQUIRE(ax.tokens_out == nullptr || (M <= kMaxRowsPerPass && ax.done_counter != nullptr),
+                AB200_E_INVALID, "head_argmax: fused token output needs M <= %d and a done counter",
+                kMaxRowsPerPass);
+  for (int64_t m0 = 0; m0 < M; m0 += kMaxRowsPerPass) {
+    const int64_t rows = M - m0 < kMaxRowsPerPass ? M - m0 : kMaxRowsPerPass;
+    const char* xp = static_cast<const char*>(x) + m0 * ldx * 2;
+    __nv_bfloat16* op = out ? out + m0 * ldo : nullptr;
+    ArgmaxExtra a = ax;
+    if (a.packed) a.packed += m0;
+    int rc;
+    if (rows <= kTileM)
+      rc = launch_gemm_pass<EPI, 1>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+    else if (rows <= 2 * kTileM)
+      rc = launch_gemm_pass<EPI, 2>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+    else
+      rc = launch_gemm_pass<EPI, 4>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+    if (rc != AB200_OK) return rc;
   }
   return AB200_OK;
 }
@@ -573,7 +689,7 @@ extern "C" int32_t ab200_linear(const void* x, const void* w, void* out, int64_t
   AB200_REQUIRE(ldo % 8 == 0 && aligned(out, 16), AB200_E_INVALID,
                 "linear: ldo must be a multiple of 8 and out 16-byte aligned");
   return launch_gemm_bf16<EPI_STORE>(x, w, M, N, K, ldx, ldw, N, static_cast<__nv_bfloat16*>(out), ldo,
-                                     nullptr, s);
+                                     ArgmaxExtra(), s);
 }
 
 extern "C" int32_t ab200_argmax_rows(const void* logits, int64_t M, int64_t N, int64_t ld,
@@ -595,8 +711,9 @@ extern "C" int32_t ab200_argmax_rows(const void* logits, int64_t M, int64_t N, i
 
 extern "C" int32_t ab200_head_argmax(const void* x, const void* w, int64_t M, int64_t w_rows,
                                      int64_t K, int64_t vocab, int64_t ldx, int64_t ldw,
-                                     uint64_t* packed_out, int32_t dtype, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+                                     uint64_t* packed_out, int64_t* tokens_out,
+                                     int64_t tokens_stride, uint32_t* done_counter, int32_t dtype,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   if (M == 0) return AB200_OK;
   AB200_REQUIRE(x && w && packed_out && M > 0 && K > 0 && vocab > 0 && vocab <= w_rows,
                 AB200_E_INVALID, "head_argmax: bad arguments");
@@ -607,11 +724,22 @@ extern "C" int32_t ab200_head_argmax(const void* x, const void* w, int64_t M, in
                   "head_argmax(f32): workspace of %zu bytes required", need);
     int rc = launch_simt<float, float>(x, w, workspace, M, vocab, K, ldx, ldw, vocab, s);
     if (rc != AB200_OK) return rc;
-    return ab200_argmax_rows(workspace, M, vocab, vocab, AB200_F32, packed_out, stream);
+    rc = ab200_argmax_rows(workspace, M, vocab, vocab, AB200_F32, packed_out, stream);
+    if (rc != AB200_OK || tokens_out == nullptr) return rc;
+    return ab200_argmax_unpack(packed_out, tokens_out, M, tokens_stride, stream);
   }
   AB200_REQUIRE(dtype == AB200_BF16, AB200_E_INVALID, "head_argmax: dtype must be bf16 or f32");
-  return launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0,
-                                      reinterpret_cast<unsigned long long*>(packed_out), s);
+  ArgmaxExtra ax;
+  ax.packed = reinterpret_cast<unsigned long long*>(packed_out);
+  if (tokens_out != nullptr && M <= kMaxRowsPerPass && done_counter != nullptr) {
+    ax.tokens_out = tokens_out;
+    ax.tokens_stride = tokens_stride;
+    ax.done_counter = done_counter;
+    return launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
+  }
+  int rc = launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
+  if (rc != AB200_OK || tokens_out == nullptr) return rc;
+  return ab200_argmax_unpack(packed_out, tokens_out, M, tokens_stride, stream);
 }
 
 extern "C" int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
@@ -627,7 +755,7 @@ extern "C" int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_o
 
 // Tile width the tcgen05 GEMM would choose for N output features on `sms` SMs (bench reporting).
 extern "C" int32_t ab200_gemm_block_n(int64_t N, int32_t sms) {
-  return pick_block_n(N, sms > 0 ? sms : sm_count());
+  return pick_block_n(N, sms > 0 ? sms : sm_count(), kMaxBlockN);
 }
 
 // bf16-input SIMT GEMM with fp32 accumulation, bf16 output: test/debug comparator for the tcgen05

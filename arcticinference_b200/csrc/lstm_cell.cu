@@ -40,6 +40,8 @@ rms_scale_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t cols, int64
   T* yr = y + row * ldy;
   float v[ITEMS][VN];
   float ss = 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int vi = threadIdx.x + it * blockDim.x;
@@ -78,12 +80,20 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
                      const T* __restrict__ wc, const T* __restrict__ bc,
                      const T* __restrict__ ws, const T* __restrict__ bs,
                      T* __restrict__ state_out, T* cell_out, int32_t D, int64_t vocab,
-                     float alpha, float eps) {
+                     float alpha, float eps, unsigned long long* __restrict__ clear_packed,
+                     unsigned int* __restrict__ clear_counter) {
   constexpr int VN = Vec16<T>::N;
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
   const int nvec = D / VN;
 
+  pdl_launch_dependents();   // the head GEMM may start prefetching its weights now
+  pdl_wait();                // gate pre-activations / previous arg-max are complete and visible
+  if (threadIdx.x == 0) {
+    // prepare this step's arg-max slot and completion counter for the head kernel that follows
+    if (clear_packed) clear_packed[row] = 0ull;
+    if (clear_counter && row == 0) *clear_counter = 0u;
+  }
   int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
   tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);  // never read outside the table
 
@@ -196,11 +206,12 @@ static int launch_rms(const void* x, void* y, int64_t rows, int64_t cols, int64_
                 "rms_scale: cols %lld too large", (long long)cols);
   const T* xp = static_cast<const T*>(x);
   T* yp = static_cast<T*>(y);
-  dim3 grid(static_cast<unsigned>(rows));
+  LaunchCfg lc(dim3(static_cast<unsigned>(rows)), dim3(threads), 0, s);
+  const int icols = static_cast<int>(cols);
   switch (items) {
-    case 1: rms_scale_kernel<T, EMU, 1><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
-    case 2: rms_scale_kernel<T, EMU, 2><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
-    default: rms_scale_kernel<T, EMU, 4><<<grid, threads, 0, s>>>(xp, yp, (int)cols, ldx, ldy, eps, post_scale); break;
+    case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 1>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
+    case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 2>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
+    default: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 4>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
   }
   AB200_CHECK_LAUNCH("rms_scale_kernel");
   return AB200_OK;
@@ -211,21 +222,31 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
                        const uint64_t* packed, const void* cell_prev, const void* wc,
                        const void* bc, const void* ws, const void* bs, void* state_out,
                        void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
-                       cudaStream_t s) {
+                       uint64_t* clear_packed, uint32_t* clear_counter, cudaStream_t s) {
   int threads, items;
   AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
                 "sum_lstm_cell: D %lld too large", (long long)D);
-  dim3 grid(static_cast<unsigned>(B));
-#define AB200_CELL_ARGS                                                                        \
-  static_cast<const T*>(gates), ldg, static_cast<const T*>(emb), tokens,                       \
-      reinterpret_cast<const unsigned long long*>(packed), static_cast<const T*>(cell_prev),   \
-      static_cast<const T*>(wc), static_cast<const T*>(bc), static_cast<const T*>(ws),         \
-      static_cast<const T*>(bs), static_cast<T*>(state_out), static_cast<T*>(cell_out), (int)D, \
-      vocab, alpha, eps
+  LaunchCfg lc(dim3(static_cast<unsigned>(B)), dim3(threads), 0, s);
+  const T* a_gates = static_cast<const T*>(gates);
+  const T* a_emb = static_cast<const T*>(emb);
+  const unsigned long long* a_packed = reinterpret_cast<const unsigned long long*>(packed);
+  const T* a_cprev = static_cast<const T*>(cell_prev);
+  const T* a_wc = static_cast<const T*>(wc);
+  const T* a_bc = static_cast<const T*>(bc);
+  const T* a_ws = static_cast<const T*>(ws);
+  const T* a_bs = static_cast<const T*>(bs);
+  T* a_state = static_cast<T*>(state_out);
+  T* a_cell = static_cast<T*>(cell_out);
+  const int32_t a_D = static_cast<int32_t>(D);
+  unsigned long long* a_clear = reinterpret_cast<unsigned long long*>(clear_packed);
+  unsigned int* a_cnt = reinterpret_cast<unsigned int*>(clear_counter);
+#define AB200_CELL_ARGS                                                                          \
+  a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
+      vocab, alpha, eps, a_clear, a_cnt
   switch (items) {
-    case 1: sum_lstm_cell_kernel<T, EMU, 1><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
-    case 2: sum_lstm_cell_kernel<T, EMU, 2><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
-    default: sum_lstm_cell_kernel<T, EMU, 4><<<grid, threads, 0, s>>>(AB200_CELL_ARGS); break;
+    case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 1>, AB200_CELL_ARGS)); break;
+    case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 2>, AB200_CELL_ARGS)); break;
+    default: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 4>, AB200_CELL_ARGS)); break;
   }
 #undef AB200_CELL_ARGS
   AB200_CHECK_LAUNCH("sum_lstm_cell_kernel");
@@ -268,7 +289,8 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
                                        const void* state_ln_weight, const void* state_ln_bias,
                                        void* state_out, void* cell_out, int64_t B, int64_t D,
                                        int64_t vocab, float alpha, float eps, int32_t dtype,
-                                       int32_t emulate_eager_rounding, void* stream) {
+                                       int32_t emulate_eager_rounding, uint64_t* clear_packed,
+                                       uint32_t* clear_counter, void* stream) {
   if (B == 0) return AB200_OK;
   AB200_REQUIRE(gates && emb_table && (tokens || packed_argmax) && cell_ln_weight &&
                     cell_ln_bias && state_ln_weight && state_ln_bias && state_out && cell_out,
@@ -286,7 +308,8 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
   const bool emu = emulate_eager_rounding != 0;
 #define AB200_ARGS                                                                               \
   gates, gates_row_stride, emb_table, tokens, packed_argmax, cell_prev, cell_ln_weight,          \
-      cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, s
+      cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, \
+      clear_packed, clear_counter, s
   switch (dtype) {
     case AB200_F32: return launch_cell<float, false>(AB200_ARGS);
     case AB200_BF16:

@@ -1,8 +1,11 @@
 // speculator.cu - library plumbing (error string, launch counter) and the whole-loop entry point
 // ab200_lstm_propose: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + arg-max) -> token unpack.
 // Replaces ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751): ~35 ATen
-// launches per step in the reference become 3 (plus ln0, one memset and one unpack per call),
-// all enqueued on one stream so the caller can capture the loop into a single CUDA graph.
+// launches per step in the reference become 3 (plus ln0 once per call), chained with programmatic
+// dependent launch and enqueued on one stream so the caller can capture the loop into a single
+// CUDA graph.  The arg-max slots are reset by the cell kernel and the int64 tokens are written by
+// the last CTA of the head kernel, so there is no memset node and no unpack launch (bf16, B<=512).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -19,6 +22,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // tokens_out[b * S + s] = token of packed[s * B + b]
 __global__ void unpack_steps_kernel(const unsigned long long* __restrict__ packed,
@@ -33,7 +44,7 @@ __global__ void unpack_steps_kernel(const unsigned long long* __restrict__ packe
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t x0, gates, state[2], cell, packed, logits, total;
+  size_t x0, gates, state[2], cell, packed, counters, logits, total;
 };
 
 static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
@@ -51,6 +62,7 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
   w.state[1] = take(static_cast<size_t>(B) * sp->inner_dim * e);
   w.cell = take(static_cast<size_t>(B) * sp->inner_dim * e);
   w.packed = take(static_cast<size_t>(B) * S * sizeof(uint64_t));
+  w.counters = take(static_cast<size_t>(S) * sizeof(uint32_t));
   w.logits = take(sp->dtype == AB200_F32 ? static_cast<size_t>(B) * sp->vocab * sizeof(float) : 0);
   w.total = off;
   return w;
@@ -61,7 +73,7 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
 using namespace ab200;
 
 extern "C" const char* ab200_last_error(void) { return g_err; }
-extern "C" int32_t ab200_abi_version(void) { return 1; }
+extern "C" int32_t ab200_abi_version(void) { return 2; }
 extern "C" int64_t ab200_launch_count(void) { return g_launches; }
 
 extern "C" size_t ab200_lstm_workspace_bytes(const ab200_lstm_speculator* spec, int64_t B,
@@ -98,7 +110,12 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
   const size_t bd = static_cast<size_t>(B) * D * e;
   uint64_t* packed = reinterpret_cast<uint64_t*>(ws + w.packed);
 
-  AB200_CUDA_OK(cudaMemsetAsync(packed, 0, static_cast<size_t>(B) * num_steps * sizeof(uint64_t), s));
+  uint32_t* counters = reinterpret_cast<uint32_t*>(ws + w.counters);
+  // bf16, B <= 512: the cell kernel resets the arg-max slot / counter of its step and the head
+  // kernel's last CTA writes the int64 tokens -> no memset node, no unpack launch.
+  const bool fused_tokens = sp->dtype == AB200_BF16 && B <= 512;
+  if (!fused_tokens)
+    AB200_CUDA_OK(cudaMemsetAsync(packed, 0, static_cast<size_t>(B) * num_steps * sizeof(uint64_t), s));
 
   const void* xin = hidden;
   int64_t ldx = ld_hidden;
@@ -123,19 +140,25 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
                              step == 0 ? nullptr : packed + static_cast<size_t>(step - 1) * B,
                              cell_prev, sp->cell_ln_w, sp->cell_ln_b, sp->state_ln_w, sp->state_ln_b,
                              state, cell, B, D, sp->vocab, sp->alpha, sp->eps, sp->dtype,
-                             sp->emulate_eager_rounding, stream);
+                             sp->emulate_eager_rounding,
+                             fused_tokens ? packed + static_cast<size_t>(step) * B : nullptr,
+                             fused_tokens ? counters + step : nullptr, stream);
     if (rc != AB200_OK) return rc;
     rc = ab200_head_argmax(state, sp->head, B, sp->head_rows, D, sp->vocab, D, D,
-                           packed + static_cast<size_t>(step) * B, sp->dtype, ws + w.logits,
+                           packed + static_cast<size_t>(step) * B,
+                           fused_tokens ? tokens_out + step : nullptr, num_steps,
+                           fused_tokens ? counters + step : nullptr, sp->dtype, ws + w.logits,
                            w.total - w.logits, stream);
     if (rc != AB200_OK) return rc;
     xin = state;
     ldx = D;
     cell_prev = cell;
   }
-  const int64_t n = B * num_steps;
-  unpack_steps_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
-      reinterpret_cast<const unsigned long long*>(packed), tokens_out, B, num_steps);
-  AB200_CHECK_LAUNCH("unpack_steps_kernel");
+  if (!fused_tokens) {
+    const int64_t n = B * num_steps;
+    unpack_steps_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(packed), tokens_out, B, num_steps);
+    AB200_CHECK_LAUNCH("unpack_steps_kernel");
+  }
   return AB200_OK;
 }

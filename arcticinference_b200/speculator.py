@@ -237,7 +237,7 @@ class ArcticLSTMSpeculator:
                 p["cell_ln.0.weight"].data_ptr(), p["cell_ln.0.bias"].data_ptr(),
                 p["state_ln.0.weight"].data_ptr(), p["state_ln.0.bias"].data_ptr(),
                 state.data_ptr(), cell.data_ptr(), B, D, self.vocab_size, self.alpha, self.eps,
-                code, emu, stream), "ab200_sum_lstm_cell")
+                code, emu, None, None, stream), "ab200_sum_lstm_cell")
         return state.unsqueeze(1), cell.unsqueeze(1)
 
     def greedy_tokens(self, states: torch.Tensor) -> torch.Tensor:
@@ -246,7 +246,7 @@ class ArcticLSTMSpeculator:
         lib, head = self._lib, self._params["head.0.weight"]
         B, D = states.shape
         states = states.contiguous()
-        packed = torch.zeros(B, dtype=torch.int64, device=self.device)
+        packed = torch.zeros(B + 1, dtype=torch.int64, device=self.device)   # [B] slots + done counter
         out = torch.empty(B, dtype=torch.long, device=self.device)
         code = _capi.torch_dtype_code(self.dtype)
         ws = None
@@ -256,12 +256,11 @@ class ArcticLSTMSpeculator:
         with torch.cuda.device(self.device):
             _capi.check(lib.ab200_head_argmax(states.data_ptr(), head.data_ptr(), B, head.shape[0], D,
                                               self.vocab_size, states.stride(0), head.stride(0),
-                                              packed.data_ptr(), code,
+                                              packed.data_ptr(), out.data_ptr(), 1,
+                                              packed[B:].data_ptr(), code,
                                               ws.data_ptr() if ws is not None else None,
                                               ws.numel() * 4 if ws is not None else 0, stream),
                         "ab200_head_argmax")
-            _capi.check(lib.ab200_argmax_unpack(packed.data_ptr(), out.data_ptr(), B, 1, stream),
-                        "ab200_argmax_unpack")
         return out
 
     def generate_token_ids(self, batch_size: int, num_predict_tokens: int, last_tokens: torch.Tensor,
@@ -283,7 +282,7 @@ class ArcticLSTMSpeculator:
     def generate_proposals(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor,
                            num_predict_tokens: int) -> torch.Tensor:
         """arctic_speculator.py:753-866: static buffers, batch padded to ``padding_size(B)``, one
-        CUDA graph per (padded batch, S) holding the whole S-step loop (3S+2 kernels + a memset)."""
+        CUDA graph per (padded batch, S) holding the whole S-step loop (3S+1 kernels, PDL-chained)."""
         if num_predict_tokens > self.max_speculative_tokens:
             raise ValueError(f"Max speculative tokens for model is "
                              f"{self.max_speculative_tokens}, but "

@@ -201,6 +201,8 @@ def time_kernels_in_sequence(model, ids, hid, iters: int):
     state = torch.empty(B, D, dtype=torch.bfloat16, device=dev)
     cell = torch.zeros(B, D, dtype=torch.bfloat16, device=dev)
     packed = torch.zeros(S, B, dtype=torch.int64, device=dev)
+    counters = torch.zeros(S, dtype=torch.int32, device=dev)
+    toks = torch.zeros(S, B, dtype=torch.int64, device=dev)
     acc = {"rms_scale": [], "gate_gemm": [], "cell": [], "head_argmax": []}
 
     def timed(name, fn):
@@ -231,10 +233,10 @@ def time_kernels_in_sequence(model, ids, hid, iters: int):
                 packed[s - 1].data_ptr() if s else None, cell.data_ptr(), p["cell_ln.0.weight"].data_ptr(),
                 p["cell_ln.0.bias"].data_ptr(), p["state_ln.0.weight"].data_ptr(),
                 p["state_ln.0.bias"].data_ptr(), state.data_ptr(), cell.data_ptr(), B, D, V, model.alpha,
-                1e-6, code, 1, st))
+                1e-6, code, 1, packed[s].data_ptr(), counters[s:].data_ptr(), st))
             timed("head_argmax", lambda: lib.ab200_head_argmax(
                 state.data_ptr(), p["head.0.weight"].data_ptr(), B, p["head.0.weight"].shape[0], D, V, D, D,
-                packed[s].data_ptr(), code, None, 0, st))
+                packed[s].data_ptr(), toks[s].data_ptr(), 1, counters[s:].data_ptr(), code, None, 0, st))
             x = state
         torch.cuda.synchronize(dev)
     return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in acc.items()}
@@ -326,6 +328,11 @@ def run_ours(args):
 
     with ClockSampler(local_rank) as clocks:
         # ---- device-timed: inputs resident in HBM, whole loop = one CUDA-graph replay ----
+        # pre-warm (graph capture, clocks and power state settle) before the W counted warm-ups
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            model.generate_proposals(ids, hid, S)
+        torch.cuda.synchronize(dev)
         for _ in range(max(args.warmup, 3)):
             model.generate_proposals(ids, hid, S)
         torch.cuda.synchronize(dev)
@@ -383,7 +390,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"{world} independent replica(s), no data-path collective",
                    "l2": "inputs larger than L2: 3.57 GB of weights streamed per step vs 126 MB L2",
-                   "graph": "whole 3-step loop = 1 CUDA graph (11 kernels + 1 memset)",
+                   "graph": f"whole 3-step loop = 1 CUDA graph ({int(launches_per_step)} kernels, PDL-chained)",
                    "head_block_n": lib.ab200_gemm_block_n(V, 0), "gate_block_n": lib.ab200_gemm_block_n(4 * D, 0)},
         "per_gpu": total_units / max_ms * 1e3 / world,
         "e2e": {"value": e2e_units / e2e_ms * 1e3, "unit": UNIT,

@@ -105,6 +105,8 @@ AB200_API int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t 
  *              when non-NULL it is the token source and `tokens` is ignored.
  *   cell_prev  [B, D] or NULL (= zeros, the first step: arctic_speculator.py:781-785)
  *   ln vectors [D]; outputs state_out, cell_out [B, D] (cell_out may alias cell_prev).
+ *   clear_packed [B] / clear_counter [1] (optional): zeroed by this kernel so that the head
+ *   kernel that follows finds its arg-max slot and completion counter reset (no memset node).
  * D must be a multiple of 8 (16-byte vectors). */
 AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
                             const void* emb_table, const int64_t* tokens,
@@ -115,7 +117,8 @@ AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_strid
                             void* state_out, void* cell_out,
                             int64_t B, int64_t D, int64_t vocab,
                             float alpha, float eps, int32_t dtype,
-                            int32_t emulate_eager_rounding, void* stream);
+                            int32_t emulate_eager_rounding,
+                            uint64_t* clear_packed, uint32_t* clear_counter, void* stream);
 
 /* out[M, N] = x[M, K] @ w[N, K]^T  (nn.Linear without bias).
  * Replaces: self.projs[i](prev_state), arctic_speculator.py:555-561,668 (cuBLAS in the reference).
@@ -136,11 +139,17 @@ AB200_API int32_t ab200_linear(const void* x, const void* w, void* out,
  *     packed = (order_preserving_bits(logit) << 32) | (0xFFFFFFFF - token)
  *   so that a 64-bit max picks the largest logit and, on ties, the LOWEST token id (torch.argmax).
  *   bf16: the logit is the fp32 accumulator rounded to bf16 (what the reference's GEMM returns).
+ *   tokens_out (optional): tokens_out[r * tokens_stride] = token of row r as int64.  For bf16 and
+ *     M <= 512 the last CTA to finish writes them (done_counter [1] must be zero on entry); in the
+ *     other cases a separate unpack launch follows.
+ *   Batch rows up to 512 share ONE pass over the weights (1, 2 or 4 accumulator tiles of 128 rows).
  *   f32 : needs workspace of M * vocab floats (logits are materialised), else AB200_E_WORKSPACE. */
 AB200_API int32_t ab200_head_argmax(const void* x, const void* w,
                           int64_t M, int64_t w_rows, int64_t K, int64_t vocab,
                           int64_t ldx, int64_t ldw,
-                          uint64_t* packed_out, int32_t dtype,
+                          uint64_t* packed_out,
+                          int64_t* tokens_out, int64_t tokens_stride, uint32_t* done_counter,
+                          int32_t dtype,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* tokens_out[i * out_stride] = 0xFFFFFFFF - low32(packed[i])  for i < count (int64 output). */
@@ -165,7 +174,8 @@ AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
 /* Whole draft loop: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + argmax) -> token unpack.
  * Replaces: ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751) as driven by
  * generate_proposals (arctic_speculator.py:753-866), TP = 1, unquantised head.
- * All launches go to `stream` (3*S + 3 kernels + 1 memset node), graph-capturable. */
+ * All launches go to `stream` (3*S + 1 kernels, chained with programmatic dependent launch),
+ * graph-capturable. */
 typedef struct ab200_lstm_speculator {
   int32_t dtype;            /* AB200_BF16 or AB200_F32 */
   int32_t emulate_eager_rounding;

@@ -87,7 +87,7 @@ def test_fused_cell_against_oracle(capi, B, D, V, dtype):
         gates.data_ptr(), 4 * D, w["forget_emb.0.weight"].data_ptr(), tok.data_ptr(), None,
         cprev.data_ptr(), w["cell_ln.0.weight"].data_ptr(), w["cell_ln.0.bias"].data_ptr(),
         w["state_ln.0.weight"].data_ptr(), w["state_ln.0.bias"].data_ptr(), state.data_ptr(),
-        cell.data_ptr(), B, D, V, alpha, 1e-6, capi.torch_dtype_code(dtype), 1, stream()))
+        cell.data_ptr(), B, D, V, alpha, 1e-6, capi.torch_dtype_code(dtype), 1, None, None, stream()))
     if dtype == torch.bfloat16:
         assert relerr(state, s_ref.squeeze(1)) < BF16_STATE_TOL
         assert relerr(cell, c_ref.squeeze(1)) < BF16_STATE_TOL
@@ -114,13 +114,14 @@ def test_fused_cell_without_emulation_stays_in_tolerance(capi):
         w["cell_ln.0.weight"].data_ptr(), w["cell_ln.0.bias"].data_ptr(),
         w["state_ln.0.weight"].data_ptr(), w["state_ln.0.bias"].data_ptr(), state.data_ptr(),
         cell.data_ptr(), B, D, V, O.emulated_alpha(3, D, torch.bfloat16, "cuda"), 1e-6,
-        capi.AB200_BF16, 0, stream()))
+        capi.AB200_BF16, 0, None, None, stream()))
     assert relerr(state, s_ref.squeeze(1)) < BF16_STATE_TOL
     assert relerr(cell, c_ref.squeeze(1)) < BF16_STATE_TOL
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 16, 8), (5, 256, 96), (64, 256, 64), (64, 16384, 4096), (128, 16384, 4096),
-                                   (96, 11520, 2880), (129, 4096, 512), (256, 2048, 1024), (17, 1000 // 8 * 8, 72)])
+                                   (96, 11520, 2880), (129, 4096, 512), (256, 2048, 1024), (17, 1000 // 8 * 8, 72),
+                                   (256, 16384, 4096), (257, 4096, 512), (512, 4096, 1024), (700, 2048, 256)])
 def test_tcgen05_linear_matches_cublas_and_simt(capi, M, N, K):
     torch.manual_seed(3)
     x = torch.randn(M, K, device=DEV).to(torch.bfloat16)
@@ -154,7 +155,8 @@ def test_linear_fp32_exact_mode(capi):
 
 @pytest.mark.parametrize("M,V,K", [(1, 100, 64), (64, 1000, 64), (64, 4096, 512), (5, 2051, 128),
                                    (64, 128256, 4096), (128, 128256, 4096), (200, 32000, 1024),
-                                   (64, 201088, 2880)])
+                                   (64, 201088, 2880), (256, 128256, 4096), (300, 50000, 512),
+                                   (512, 32000, 1024)])
 def test_fused_head_argmax_matches_torch(capi, M, V, K):
     """Never-materialised logits + packed atomicMax == argmax over cuBLAS bf16 logits[:, :V],
     including the lowest-index tie-break (bf16 logits tie often: SURVEY F5)."""
@@ -166,9 +168,12 @@ def test_fused_head_argmax_matches_torch(capi, M, V, K):
     packed = torch.zeros(M, dtype=torch.int64, device=DEV)
     tok = torch.empty(M, dtype=torch.long, device=DEV)
     lib = capi.lib()
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
     capi.check(lib.ab200_head_argmax(x.data_ptr(), w.data_ptr(), M, Vp, K, V, K, K, packed.data_ptr(),
-                                     capi.AB200_BF16, None, 0, stream()))
-    capi.check(lib.ab200_argmax_unpack(packed.data_ptr(), tok.data_ptr(), M, 1, stream()))
+                                     tok.data_ptr(), 1, counter.data_ptr(), capi.AB200_BF16, None, 0, stream()))
+    tok2 = torch.empty_like(tok)
+    capi.check(lib.ab200_argmax_unpack(packed.data_ptr(), tok2.data_ptr(), M, 1, stream()))
+    assert torch.equal(tok, tok2)          # last-CTA token write == separate unpack of the packed maxima
     logits = F.linear(x, w)[:, :V]
     ref = torch.argmax(logits, -1)
     agree = (tok == ref).float().mean().item()
@@ -195,7 +200,7 @@ def test_argmax_tie_break_is_lowest_index(capi):
     tok = torch.empty(M, dtype=torch.long, device=DEV)
     lib = capi.lib()
     capi.check(lib.ab200_head_argmax(x.data_ptr(), w2.data_ptr(), M, V, K, V, K, K, packed.data_ptr(),
-                                     capi.AB200_BF16, None, 0, stream()))
+                                     None, 0, None, capi.AB200_BF16, None, 0, stream()))
     capi.check(lib.ab200_argmax_unpack(packed.data_ptr(), tok.data_ptr(), M, 1, stream()))
     assert torch.equal(tok, ref)
 

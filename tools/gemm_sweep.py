@@ -25,7 +25,7 @@ for M in (8, 16, 32, 64, 128, 256):
     x = torch.randn(M, D, device=dev).to(torch.bfloat16)
     packed = torch.zeros(M, dtype=torch.int64, device=dev)
     gates = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
-    h = timeit(lambda: lib.ab200_head_argmax(x.data_ptr(), Wh.data_ptr(), M, V, D, V, D, D, packed.data_ptr(), 2, None, 0, st))
+    h = timeit(lambda: lib.ab200_head_argmax(x.data_ptr(), Wh.data_ptr(), M, V, D, V, D, D, packed.data_ptr(), None, 0, None, 2, None, 0, st))
     g = timeit(lambda: lib.ab200_linear(x.data_ptr(), Wg.data_ptr(), gates.data_ptr(), M, 4 * D, D, D, D, 4 * D, 2, st))
     cb = timeit(lambda: torch.nn.functional.linear(x, Wh))
     cg = timeit(lambda: torch.nn.functional.linear(x, Wg))

@@ -54,7 +54,7 @@ def _():
         w[:V] = (torch.randn(V, K, device=dev) * 0.02).to(torch.bfloat16)
         packed = torch.zeros(M, dtype=torch.int64, device=dev)
         tok = torch.empty(M, dtype=torch.long, device=dev)
-        rc = lib.ab200_head_argmax(x.data_ptr(), w.data_ptr(), M, Vp, K, V, K, K, packed.data_ptr(), _capi.AB200_BF16, None, 0, st())
+        rc = lib.ab200_head_argmax(x.data_ptr(), w.data_ptr(), M, Vp, K, V, K, K, packed.data_ptr(), None, 0, None, _capi.AB200_BF16, None, 0, st())
         rc2 = lib.ab200_argmax_unpack(packed.data_ptr(), tok.data_ptr(), M, 1, st())
         torch.cuda.synchronize()
         ref = torch.argmax(F.linear(x, w)[:, :V], -1)
