@@ -54,6 +54,11 @@ void count_launch(int n = 1);
 // kernel produced; both are no-ops for launches without the attribute.  AB200_PDL=0 disables it.
 bool pdl_enabled();
 
+// Optional device-side timeline (ab200_set_trace_buffer): every traced launch owns 4 u64 slots
+// {min CTA entry, min time after the PDL wait, max CTA exit, unused} of %globaltimer nanoseconds.
+// next_trace_slot() returns nullptr when tracing is off.
+unsigned long long* next_trace_slot();
+
 struct LaunchCfg {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
@@ -117,6 +122,19 @@ __device__ __forceinline__ void st_stream_16(void* p, const uint4& v) {
                : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// which: 0 = CTA entry (min), 1 = dependency resolved (min), 2 = CTA exit (max)
+__device__ __forceinline__ void trace_stamp(unsigned long long* slot, int which) {
+  if (slot != nullptr) {
+    const unsigned long long t = globaltimer_ns();
+    if (which == 2) atomicMax(slot + 2, t);
+    else atomicMin(slot + which, t);
+  }
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -168,6 +168,7 @@ struct GemmParams {
   int32_t num_k_blocks;
   int32_t stages;
   int32_t l2_prefetch_kb;  // extra W k-blocks prefetched into L2 before the dependency wait
+  int32_t pre_stages;      // smem stages filled with W before the dependency wait
   uint32_t tx_bytes;    // bytes landing per stage
   uint32_t idesc;
   __nv_bfloat16* out;   // EPI_STORE
@@ -176,6 +177,7 @@ struct GemmParams {
   int64_t* tokens_out;         // EPI_ARGMAX, optional: written by the last CTA to finish
   int64_t tokens_stride;
   unsigned int* done_counter;  // EPI_ARGMAX, zero on entry (needed iff tokens_out)
+  unsigned long long* trace;   // optional timeline slot (profiling)
 };
 
 // K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -212,6 +214,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t flag_slot = tmem_slot + 8u;
 
   if (warp == 0 && lane == 0) {
+    trace_stamp(p.trace, 0);
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
   }
@@ -261,7 +264,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       };
       // The weights do not depend on the previous kernel: fill the ring with W (and warm L2 with
       // the k-blocks after that) BEFORE waiting for the producer of x.
-      const int pre = total < stages ? total : stages;
+      const int pre = total < p.pre_stages ? total : p.pre_stages;
       for (int g = 0; g < pre; ++g) {
         mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
         load_w(g, g);
@@ -269,6 +272,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
       for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kBlockK, n0_of(g));
       pdl_wait();
+      trace_stamp(p.trace, 1);
       for (int g = 0; g < pre; ++g) load_x(g, g);
       int stage = pre == stages ? 0 : pre;
       uint32_t phase = pre == stages ? 1u : 0u;
@@ -282,7 +286,8 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    pdl_wait();
+    // (no griddepcontrol.wait here: this warp touches no global memory and is gated by the
+    //  full barriers, which complete only after the producer's post-wait x loads)
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -315,7 +320,10 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    pdl_wait();
+    // Gated by the accumulator-full barrier, i.e. transitively by the producer's dependency wait.
+    // Everything it touches from the previous kernel (packed slots, done counter) is accessed
+    // with L2 atomics only, so these warps sleep in mbarrier.try_wait instead of sitting in
+    // griddepcontrol.wait next to the (issue-bound) cell kernel that shares the SM.
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     float best[MT];
     uint32_t best_idx[MT];
@@ -413,6 +421,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) trace_stamp(p.trace, 2);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -528,6 +537,9 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
   p.stages = stages;
   p.l2_prefetch_kb = pdl_enabled() ? env_int("AB200_L2_PREFETCH_KB", 0) : 0;
+  p.pre_stages = env_int("AB200_PRE_STAGES", stages);
+  if (p.pre_stages > stages) p.pre_stages = stages;
+  if (p.pre_stages < 0) p.pre_stages = 0;
   p.tx_bytes = static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
   // instruction descriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
@@ -538,6 +550,7 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.tokens_out = ax.tokens_out;
   p.tokens_stride = ax.tokens_stride;
   p.done_counter = ax.done_counter;
+  p.trace = next_trace_slot();
   const int grid = num_n_tiles < sms ? num_n_tiles : sms;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
   LaunchCfg cfg(dim3(grid), dim3(kGemmThreads), smem, s);

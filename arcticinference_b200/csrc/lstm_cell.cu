@@ -31,7 +31,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 template <typename T, bool EMU, int ITEMS>
 __global__ void __launch_bounds__(1024)
 rms_scale_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t cols, int64_t ldx,
-                 int64_t ldy, float eps, float post_scale) {
+                 int64_t ldy, float eps, float post_scale, unsigned long long* trace) {
   constexpr int VN = Vec16<T>::N;
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
@@ -40,8 +40,10 @@ rms_scale_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t cols, int64
   T* yr = y + row * ldy;
   float v[ITEMS][VN];
   float ss = 0.f;
+  if (threadIdx.x == 0) trace_stamp(trace, 0);
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_stamp(trace, 1);
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int vi = threadIdx.x + it * blockDim.x;
@@ -69,6 +71,7 @@ rms_scale_kernel(const T* __restrict__ x, T* __restrict__ y, int32_t cols, int64
       *reinterpret_cast<uint4*>(yr + vi * VN) = out.u;
     }
   }
+  if (threadIdx.x == 0) trace_stamp(trace, 2);
 }
 
 template <typename T, bool EMU, int ITEMS>
@@ -81,15 +84,17 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
                      const T* __restrict__ ws, const T* __restrict__ bs,
                      T* __restrict__ state_out, T* cell_out, int32_t D, int64_t vocab,
                      float alpha, float eps, unsigned long long* __restrict__ clear_packed,
-                     unsigned int* __restrict__ clear_counter) {
+                     unsigned int* __restrict__ clear_counter, unsigned long long* trace) {
   constexpr int VN = Vec16<T>::N;
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
   const int nvec = D / VN;
 
+  if (threadIdx.x == 0) trace_stamp(trace, 0);
   pdl_launch_dependents();   // the head GEMM may start prefetching its weights now
   pdl_wait();                // gate pre-activations / previous arg-max are complete and visible
   if (threadIdx.x == 0) {
+    trace_stamp(trace, 1);
     // prepare this step's arg-max slot and completion counter for the head kernel that follows
     if (clear_packed) clear_packed[row] = 0ull;
     if (clear_counter && row == 0) *clear_counter = 0u;
@@ -182,6 +187,7 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
       }
     }
   }
+  if (threadIdx.x == 0) trace_stamp(trace, 2);
 }
 
 // block size / items-per-thread for a row of `nvec` 16-byte vectors
@@ -208,10 +214,11 @@ static int launch_rms(const void* x, void* y, int64_t rows, int64_t cols, int64_
   T* yp = static_cast<T*>(y);
   LaunchCfg lc(dim3(static_cast<unsigned>(rows)), dim3(threads), 0, s);
   const int icols = static_cast<int>(cols);
+  unsigned long long* tr = next_trace_slot();
   switch (items) {
-    case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 1>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
-    case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 2>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
-    default: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 4>, xp, yp, icols, ldx, ldy, eps, post_scale)); break;
+    case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 1>, xp, yp, icols, ldx, ldy, eps, post_scale, tr)); break;
+    case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 2>, xp, yp, icols, ldx, ldy, eps, post_scale, tr)); break;
+    default: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, rms_scale_kernel<T, EMU, 4>, xp, yp, icols, ldx, ldy, eps, post_scale, tr)); break;
   }
   AB200_CHECK_LAUNCH("rms_scale_kernel");
   return AB200_OK;
@@ -240,9 +247,10 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
   const int32_t a_D = static_cast<int32_t>(D);
   unsigned long long* a_clear = reinterpret_cast<unsigned long long*>(clear_packed);
   unsigned int* a_cnt = reinterpret_cast<unsigned int*>(clear_counter);
+  unsigned long long* a_trace = next_trace_slot();
 #define AB200_CELL_ARGS                                                                          \
   a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
-      vocab, alpha, eps, a_clear, a_cnt
+      vocab, alpha, eps, a_clear, a_cnt, a_trace
   switch (items) {
     case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 1>, AB200_CELL_ARGS)); break;
     case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 2>, AB200_CELL_ARGS)); break;

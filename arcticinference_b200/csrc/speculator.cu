@@ -22,6 +22,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+static unsigned long long* g_trace_base = nullptr;
+static int g_trace_cap = 0, g_trace_next = 0;
+unsigned long long* next_trace_slot() {
+  if (g_trace_base == nullptr || g_trace_next >= g_trace_cap) return nullptr;
+  return g_trace_base + 4 * static_cast<size_t>(g_trace_next++);
+}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -75,6 +81,12 @@ using namespace ab200;
 extern "C" const char* ab200_last_error(void) { return g_err; }
 extern "C" int32_t ab200_abi_version(void) { return 2; }
 extern "C" int64_t ab200_launch_count(void) { return g_launches; }
+extern "C" int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches) {
+  g_trace_base = reinterpret_cast<unsigned long long*>(device_slots);
+  g_trace_cap = device_slots ? max_launches : 0;
+  g_trace_next = 0;
+  return AB200_OK;
+}
 
 extern "C" size_t ab200_lstm_workspace_bytes(const ab200_lstm_speculator* spec, int64_t B,
                                              int32_t num_steps) {

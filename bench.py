@@ -307,7 +307,7 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:
-        replicas.init_from_env("nccl")
+        replicas.init_from_env("nccl", dev)
     V, H, D, S, B = (CFG[k] for k in "VHDSB")
     peak, peak_src = measured_peak_gbs()
 

@@ -46,6 +46,13 @@ AB200_API int32_t ab200_abi_version(void);
 /* Number of kernel launches this library has enqueued on this thread since load (bench claim). */
 AB200_API int64_t ab200_launch_count(void);
 
+/* Device-side timeline for profiling a (graph-captured) draft loop.  device_slots: 4 uint64 per
+ * traced launch, initialised by the caller to {~0, ~0, 0, 0}; each speculator kernel launched while
+ * tracing is on takes the next slot and records %globaltimer ns: [0] = earliest CTA entry,
+ * [1] = earliest time its dependency wait returned, [2] = latest CTA exit.  NULL switches it off.
+ * Process-global, not thread-safe: a profiling aid, not part of the product path. */
+AB200_API int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches);
+
 /* ------------------------------------------------------------------------------------------
  * Hot path B: SwiftKV multi-layer bulk reshape-and-cache.
  * Replaces: csrc/custom_ops/kernels.cu:86-155 (host launcher reshape_and_cache_flash_bulk) and
