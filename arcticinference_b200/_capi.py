@@ -26,6 +26,7 @@ class LstmSpeculatorDesc(ctypes.Structure):
         ("cell_ln_w", c_void_p), ("cell_ln_b", c_void_p),
         ("state_ln_w", c_void_p), ("state_ln_b", c_void_p),
         ("head", c_void_p),
+        ("head_q", c_void_p), ("head_scale", c_void_p), ("fp8_head_max_batch", c_int32),
     ]
 
 
@@ -45,7 +46,7 @@ SIGNATURES = {
     "ab200_sum_lstm_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_int32, c_int32,
-                                      c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ab200_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                c_int64, c_int64, c_int64, c_int32, c_void_p]),
     "ab200_linear_simt_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
@@ -53,6 +54,15 @@ SIGNATURES = {
     "ab200_head_argmax": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                     c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                     c_int32, c_void_p, c_size_t, c_void_p]),
+    "ab200_fp8_quantize_weight": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                            c_int64, c_void_p]),
+    "ab200_fp8_quantize_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                          c_int64, c_void_p]),
+    "ab200_linear_fp8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "ab200_head_argmax_fp8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                        c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                        c_int64, c_void_p, c_void_p]),
     "ab200_argmax_unpack": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ab200_argmax_rows": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                     c_void_p]),

@@ -3,6 +3,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -162,6 +163,33 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   float r = scratch[32];
   __syncthreads();  // scratch may be reused immediately
   return r;
+}
+
+// Block-wide max of non-negative values, broadcast. `scratch` holds >= 33 floats.
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < nwarps ? scratch[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  const float r = scratch[32];
+  __syncthreads();
+  return r;
+}
+
+// FP8 e4m3 (vLLM semantics: round-to-nearest-even, saturate to +-448)
+constexpr float kFp8Max = 448.0f;
+constexpr float kFp8MinScale = 1.0f / (448.0f * 512.0f);
+__device__ __forceinline__ uint8_t to_e4m3(float v) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
 }
 
 // Packed (value, index) for a 64-bit max: larger logit wins; equal logits -> lower index wins.

@@ -104,15 +104,27 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
                : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, single CTA, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T, single CTA, fp32 accumulate.
+// KIND 0: bf16 x bf16 (kind::f16, K = 16 per instruction); KIND 1: e4m3 x e4m3 (kind::f8f6f4, K = 32)
+enum { KIND_BF16 = 0, KIND_FP8 = 1 };
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                     uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND == KIND_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -145,8 +157,9 @@ __device__ __forceinline__ bool elect_one() {
 // ------------------------------------------------------------------------------------------
 // tcgen05 weight-streaming GEMM
 // ------------------------------------------------------------------------------------------
-constexpr int kBlockK = 64;   // 64 bf16 = 128 B: one SWIZZLE_128B row
-constexpr int kUmmaK = 16;
+constexpr int kRowBytes = 128;  // one SWIZZLE_128B row = one k-block: 64 bf16 or 128 e4m3 elements
+constexpr int kBlockK = 64;     // bf16 elements per k-block (fp8: 128)
+constexpr int kUmmaK = 16;      // bf16 elements per MMA (fp8: 32); both are 32 bytes of the row
 constexpr int kTileM = 128;   // UMMA M = TMEM lanes = batch rows per m-tile
 constexpr int kMaxBlockN = 256;
 constexpr int kGemmThreads = 192;
@@ -169,6 +182,7 @@ struct GemmParams {
   int32_t stages;
   int32_t l2_prefetch_kb;  // extra W k-blocks prefetched into L2 before the dependency wait
   int32_t pre_stages;      // smem stages filled with W before the dependency wait
+  int32_t late_trigger;    // 1: griddepcontrol.launch_dependents after the last TMA load
   uint32_t tx_bytes;    // bytes landing per stage
   uint32_t idesc;
   __nv_bfloat16* out;   // EPI_STORE
@@ -178,6 +192,8 @@ struct GemmParams {
   int64_t tokens_stride;
   unsigned int* done_counter;  // EPI_ARGMAX, zero on entry (needed iff tokens_out)
   unsigned long long* trace;   // optional timeline slot (profiling)
+  const float* x_scales;       // KIND_FP8: per-row activation scales [m_rows]
+  const float* w_scale;        // KIND_FP8: per-tensor weight scale [1]
 };
 
 // K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -192,12 +208,13 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 
 // MT = number of 128-row m-tiles (batch rows up to MT*128) that share ONE pass over the weights.
-template <int EPI, int MT>
+template <int EPI, int MT, int KIND>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
+gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   constexpr int kAccSlot = kMaxBlockN / MT;   // TMEM columns per (buffer, m-tile); block_n <= kAccSlot
   constexpr uint32_t kASlot = MT * kABytes;
+  constexpr int kKElems = KIND == KIND_BF16 ? 64 : 128;   // elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -239,9 +256,11 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // Programmatic dependent launch: let the next kernel in the stream start its own prologue now;
-  // it blocks in griddepcontrol.wait until this grid has completed and flushed.
-  pdl_launch_dependents();
+  // Programmatic dependent launch: the next kernel in the stream may start its prologue once every
+  // CTA of this grid has signalled (it still blocks in griddepcontrol.wait until this grid has
+  // completed and flushed).  late_trigger: signal only after this CTA has issued its last TMA
+  // load, so that the dependent's launch overlaps just the tail of this kernel.
+  if (!p.late_trigger) pdl_launch_dependents();
 
   const int num_kb = p.num_k_blocks;
   const int my_tiles = static_cast<int>(blockIdx.x) < p.num_n_tiles
@@ -256,11 +275,11 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
         const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
         for (int t = 0; t < MT; ++t)
-          tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK, t * kTileM, kEvictLast);
+          tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
       };
       auto load_w = [&](int g, int stage) {
         const uint32_t sa = smem_base + stage * stage_bytes;
-        tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK, n0_of(g), kEvictFirst);
+        tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
       };
       // The weights do not depend on the previous kernel: fill the ring with W (and warm L2 with
       // the k-blocks after that) BEFORE waiting for the producer of x.
@@ -270,7 +289,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
         load_w(g, g);
       }
       const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
-      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kBlockK, n0_of(g));
+      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
       pdl_wait();
       trace_stamp(p.trace, 1);
       for (int g = 0; g < pre; ++g) load_x(g, g);
@@ -283,6 +302,7 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
         load_w(g, stage);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
+      if (p.late_trigger) pdl_launch_dependents();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -306,9 +326,9 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
             const uint64_t da = smem_desc_sw128(sa + t * kABytes);
             const uint32_t tmem_d = tmem_base + (acc * MT + t) * kAccSlot;
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-              umma_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // one MMA consumes 32 B of the 128 B swizzle row: +2 in the (>>4) address field
+              umma<KIND>(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(stage));                      // smem stage reusable once MMAs retire
@@ -329,12 +349,25 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     uint32_t best_idx[MT];
 #pragma unroll
     for (int t = 0; t < MT; ++t) { best[t] = -INFINITY; best_idx[t] = 0xFFFFFFFFu; }
+    float sa[MT], sb = 1.0f;   // fp8: out = s_x[row] * (s_w * acc), the order of vLLM's ScaledEpilogue
+    bool scales_loaded = false;
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int n0 = (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * p.block_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if constexpr (KIND == KIND_FP8) {
+        if (!scales_loaded) {   // produced by the previous kernel: read (L2) only after the barrier
+          scales_loaded = true;
+          sb = __ldcg(p.w_scale);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const int r = t * kTileM + quad * 32 + lane;
+            sa[t] = r < p.m_rows ? __ldcg(p.x_scales + r) : 0.f;
+          }
+        }
+      }
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         const int row = t * kTileM + quad * 32 + lane;   // batch row inside the pass
@@ -345,6 +378,10 @@ gemm_bf16_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
           tmem_ld_wait();
+          if constexpr (KIND == KIND_FP8) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(sa[t] * (sb * __uint_as_float(r[j])));
+          }
           const int col0 = n0 + c0;
           if constexpr (EPI == EPI_STORE) {
             if (row_ok && col0 < p.n_valid) {
@@ -445,16 +482,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, K] matrix (row stride ld), box = [box_rows x 64]
+// 2-D tensor map over a row-major [rows, K] matrix (row stride ld elements of esize bytes),
+// box = [box_rows x 128 bytes]
 static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld,
-                     int box_rows) {
+                     int box_rows, int esize) {
   EncodeTiledFn enc = get_encode_fn();
   AB200_REQUIRE(enc != nullptr, AB200_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kRowBytes / esize), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(base), gdim, gstr, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AB200_REQUIRE(r == CUDA_SUCCESS, AB200_E_CUDA,
@@ -502,15 +541,17 @@ struct ArgmaxExtra {
   int64_t* tokens_out = nullptr;
   int64_t tokens_stride = 0;
   unsigned int* done_counter = nullptr;
+  const float* x_scales = nullptr;   // KIND_FP8
+  const float* w_scale = nullptr;    // KIND_FP8
 };
 
-template <int EPI, int MT>
+template <int EPI, int MT, int KIND>
 static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
                             int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_sm100<EPI, MT>,
+    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100<EPI, MT, KIND>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
@@ -523,10 +564,12 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   if (stages > kMaxStages) stages = kMaxStages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
 
+  constexpr int esize = KIND == KIND_BF16 ? 2 : 1;
+  constexpr int k_elems = kRowBytes / esize;
   CUtensorMap tmx, tmw;
-  int rc = make_tmap(&tmx, x, m_rows, K, ldx, box_m);
+  int rc = make_tmap(&tmx, x, m_rows, K, ldx, box_m, esize);
   if (rc != AB200_OK) return rc;
-  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn);
+  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn, esize);
   if (rc != AB200_OK) return rc;
 
   GemmParams p;
@@ -534,16 +577,21 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.n_valid = static_cast<int32_t>(n_valid);
   p.block_n = bn;
   p.num_n_tiles = num_n_tiles;
-  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
+  p.num_k_blocks = static_cast<int32_t>((K + k_elems - 1) / k_elems);
   p.stages = stages;
   p.l2_prefetch_kb = pdl_enabled() ? env_int("AB200_L2_PREFETCH_KB", 0) : 0;
+  p.late_trigger = env_int("AB200_LATE_TRIGGER", 1);
   p.pre_stages = env_int("AB200_PRE_STAGES", stages);
   if (p.pre_stages > stages) p.pre_stages = stages;
   if (p.pre_stages < 0) p.pre_stages = 0;
   p.tx_bytes = static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
-  // instruction descriptor: D=f32 [4,6), A=bf16 [7,10), B=bf16 [10,13), K-major A/B, N>>3 [17,23), M>>4 [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+  // instruction descriptor: D=f32 [4,6), A/B format [7,10)/[10,13) (kind::f16: 1 = bf16;
+  // kind::f8f6f4: 0 = e4m3), K-major A/B, N>>3 [17,23), M>>4 [24,29)
+  const uint32_t fmt = KIND == KIND_BF16 ? 1u : 0u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
             (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.x_scales = ax.x_scales;
+  p.w_scale = ax.w_scale;
   p.out = out;
   p.ldo = ldo;
   p.packed = ax.packed;
@@ -554,18 +602,22 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   const int grid = num_n_tiles < sms ? num_n_tiles : sms;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
   LaunchCfg cfg(dim3(grid), dim3(kGemmThreads), smem, s);
-  AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_bf16_tn_sm100<EPI, MT>, tmx, tmw, p));
-  AB200_CHECK_LAUNCH("gemm_bf16_tn_sm100");
+  AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_tn_sm100<EPI, MT, KIND>, tmx, tmw, p));
+  AB200_CHECK_LAUNCH("gemm_tn_sm100");
   return AB200_OK;
 }
 
-template <int EPI>
+template <int EPI, int KIND = KIND_BF16>
 static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
                             int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
-  AB200_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && aligned(x, 16) && aligned(w, 16),
+  constexpr int kAlign = KIND == KIND_BF16 ? 8 : 16;   // 16-byte rows / strides
+  constexpr int esize = KIND == KIND_BF16 ? 2 : 1;
+  AB200_REQUIRE(K % kAlign == 0 && ldx % kAlign == 0 && ldw % kAlign == 0 && aligned(x, 16) && aligned(w, 16),
                 AB200_E_INVALID,
-                "bf16 GEMM: K, ldx, ldw must be multiples of 8 and x/w 16-byte aligned");
+                "tcgen05 GEMM: K, ldx, ldw must be multiples of %d and x/w 16-byte aligned", kAlign);
+  AB200_REQUIRE(KIND == KIND_BF16 || (ax.x_scales != nullptr && ax.w_scale != nullptr), AB200_E_INVALID,
+                "fp8 GEMM: scales required");
   AB200_REQUIRE(M > 0 && w_rows > 0 && K > 0 && n_valid > 0 && n_valid <= w_rows &&
                     w_rows < (1LL << 31) && K < (1LL << 31),
                 AB200_E_INVALID, "bf16 GEMM: bad sizes");
@@ -574,17 +626,18 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
                 kMaxRowsPerPass);
   for (int64_t m0 = 0; m0 < M; m0 += kMaxRowsPerPass) {
     const int64_t rows = M - m0 < kMaxRowsPerPass ? M - m0 : kMaxRowsPerPass;
-    const char* xp = static_cast<const char*>(x) + m0 * ldx * 2;
+    const char* xp = static_cast<const char*>(x) + m0 * ldx * esize;
     __nv_bfloat16* op = out ? out + m0 * ldo : nullptr;
     ArgmaxExtra a = ax;
     if (a.packed) a.packed += m0;
+    if (a.x_scales) a.x_scales += m0;
     int rc;
     if (rows <= kTileM)
-      rc = launch_gemm_pass<EPI, 1>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+      rc = launch_gemm_pass<EPI, 1, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else if (rows <= 2 * kTileM)
-      rc = launch_gemm_pass<EPI, 2>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+      rc = launch_gemm_pass<EPI, 2, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else
-      rc = launch_gemm_pass<EPI, 4>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+      rc = launch_gemm_pass<EPI, 4, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     if (rc != AB200_OK) return rc;
   }
   return AB200_OK;
@@ -751,6 +804,48 @@ extern "C" int32_t ab200_head_argmax(const void* x, const void* w, int64_t M, in
     return launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
   }
   int rc = launch_gemm_bf16<EPI_ARGMAX>(x, w, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
+  if (rc != AB200_OK || tokens_out == nullptr) return rc;
+  return ab200_argmax_unpack(packed_out, tokens_out, M, tokens_stride, stream);
+}
+
+// FP8 (e4m3 x e4m3 -> fp32) projections: out = bf16(x_scales[row] * (w_scale * acc)).
+extern "C" int32_t ab200_linear_fp8(const void* xq, const float* x_scales, const void* wq,
+                                    const float* w_scale, void* out, int64_t M, int64_t N, int64_t K,
+                                    int64_t ldx, int64_t ldw, int64_t ldo, void* stream) {
+  if (M == 0 || N == 0) return AB200_OK;
+  AB200_REQUIRE(xq && x_scales && wq && w_scale && out && M > 0 && N > 0 && K > 0, AB200_E_INVALID,
+                "linear_fp8: bad arguments");
+  AB200_REQUIRE(ldo % 8 == 0 && aligned(out, 16), AB200_E_INVALID,
+                "linear_fp8: ldo must be a multiple of 8 and out 16-byte aligned");
+  ArgmaxExtra ax;
+  ax.x_scales = x_scales;
+  ax.w_scale = w_scale;
+  return launch_gemm_bf16<EPI_STORE, KIND_FP8>(xq, wq, M, N, K, ldx, ldw, N,
+                                               static_cast<__nv_bfloat16*>(out), ldo, ax,
+                                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, const void* wq,
+                                         const float* w_scale, int64_t M, int64_t w_rows, int64_t K,
+                                         int64_t vocab, int64_t ldx, int64_t ldw, uint64_t* packed_out,
+                                         int64_t* tokens_out, int64_t tokens_stride,
+                                         uint32_t* done_counter, void* stream) {
+  if (M == 0) return AB200_OK;
+  AB200_REQUIRE(xq && x_scales && wq && w_scale && packed_out && M > 0 && K > 0 && vocab > 0 &&
+                    vocab <= w_rows,
+                AB200_E_INVALID, "head_argmax_fp8: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ArgmaxExtra ax;
+  ax.packed = reinterpret_cast<unsigned long long*>(packed_out);
+  ax.x_scales = x_scales;
+  ax.w_scale = w_scale;
+  if (tokens_out != nullptr && M <= kMaxRowsPerPass && done_counter != nullptr) {
+    ax.tokens_out = tokens_out;
+    ax.tokens_stride = tokens_stride;
+    ax.done_counter = done_counter;
+    return launch_gemm_bf16<EPI_ARGMAX, KIND_FP8>(xq, wq, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
+  }
+  int rc = launch_gemm_bf16<EPI_ARGMAX, KIND_FP8>(xq, wq, M, w_rows, K, ldx, ldw, vocab, nullptr, 0, ax, s);
   if (rc != AB200_OK || tokens_out == nullptr) return rc;
   return ab200_argmax_unpack(packed_out, tokens_out, M, tokens_stride, stream);
 }

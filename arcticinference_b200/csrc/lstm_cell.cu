@@ -84,7 +84,8 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
                      const T* __restrict__ ws, const T* __restrict__ bs,
                      T* __restrict__ state_out, T* cell_out, int32_t D, int64_t vocab,
                      float alpha, float eps, unsigned long long* __restrict__ clear_packed,
-                     unsigned int* __restrict__ clear_counter, unsigned long long* trace) {
+                     unsigned int* __restrict__ clear_counter, unsigned long long* trace,
+                     uint8_t* __restrict__ state_q, float* __restrict__ state_scale) {
   constexpr int VN = Vec16<T>::N;
   __shared__ float scratch[33];
   const int64_t row = blockIdx.x;
@@ -162,6 +163,7 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
   }
   // state_ln (RMS, affine) -> GELU -> * output gate
   ss = block_sum(ss, scratch);
+  float amax = 0.f;
   {
     const float mean = R<T, EMU>(ss * inv_d);
     const float inv = R<T, EMU>(rsqrtf(R<T, EMU>(mean + eps)));
@@ -181,9 +183,32 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
           y = R<T, EMU>(y * og[it][j]);
           so.e[j] = ST<T>::from_f(y);
           co.e[j] = ST<T>::from_f(c[it][j]);
+          f[it][j] = ST<T>::to_f(so.e[j]);   // the stored (rounded) state, for the fp8 copy below
+          amax = fmaxf(amax, fabsf(f[it][j]));
         }
         *reinterpret_cast<uint4*>(state_out + row * D + vi * VN) = so.u;
         *reinterpret_cast<uint4*>(cell_out + row * D + vi * VN) = co.u;
+      }
+    }
+  }
+  if (state_q != nullptr) {
+    // Dynamic per-token FP8 copy of the state for the quantised head (what the reference's qhead
+    // does inside Fp8LinearOp.apply): s = max(amax/448, 1/(448*512)), q = sat_e4m3(x / s).
+    amax = block_max(amax, scratch);
+    const float scale = fmaxf(amax / kFp8Max, kFp8MinScale);
+    if (threadIdx.x == 0) state_scale[row] = scale;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (vi < nvec) {
+        uint8_t qv[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) qv[j] = to_e4m3(f[it][j] / scale);
+        if constexpr (VN == 8) {
+          *reinterpret_cast<uint2*>(state_q + row * D + vi * VN) = *reinterpret_cast<uint2*>(qv);
+        } else {
+          *reinterpret_cast<uint32_t*>(state_q + row * D + vi * VN) = *reinterpret_cast<uint32_t*>(qv);
+        }
       }
     }
   }
@@ -229,7 +254,8 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
                        const uint64_t* packed, const void* cell_prev, const void* wc,
                        const void* bc, const void* ws, const void* bs, void* state_out,
                        void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
-                       uint64_t* clear_packed, uint32_t* clear_counter, cudaStream_t s) {
+                       uint64_t* clear_packed, uint32_t* clear_counter, void* state_q,
+                       float* state_scale, cudaStream_t s) {
   int threads, items;
   AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
                 "sum_lstm_cell: D %lld too large", (long long)D);
@@ -248,9 +274,10 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
   unsigned long long* a_clear = reinterpret_cast<unsigned long long*>(clear_packed);
   unsigned int* a_cnt = reinterpret_cast<unsigned int*>(clear_counter);
   unsigned long long* a_trace = next_trace_slot();
+  uint8_t* a_sq = static_cast<uint8_t*>(state_q);
 #define AB200_CELL_ARGS                                                                          \
   a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
-      vocab, alpha, eps, a_clear, a_cnt, a_trace
+      vocab, alpha, eps, a_clear, a_cnt, a_trace, a_sq, state_scale
   switch (items) {
     case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 1>, AB200_CELL_ARGS)); break;
     case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 2>, AB200_CELL_ARGS)); break;
@@ -298,12 +325,16 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
                                        void* state_out, void* cell_out, int64_t B, int64_t D,
                                        int64_t vocab, float alpha, float eps, int32_t dtype,
                                        int32_t emulate_eager_rounding, uint64_t* clear_packed,
-                                       uint32_t* clear_counter, void* stream) {
+                                       uint32_t* clear_counter, void* state_q_out,
+                                       float* state_scale_out, void* stream) {
   if (B == 0) return AB200_OK;
   AB200_REQUIRE(gates && emb_table && (tokens || packed_argmax) && cell_ln_weight &&
                     cell_ln_bias && state_ln_weight && state_ln_bias && state_out && cell_out,
                 AB200_E_INVALID, "sum_lstm_cell: NULL pointer argument");
   AB200_REQUIRE(B > 0 && D > 0 && vocab > 0, AB200_E_INVALID, "sum_lstm_cell: bad sizes");
+  AB200_REQUIRE(state_q_out == nullptr || (state_scale_out != nullptr && dtype == AB200_BF16 &&
+                                            aligned(state_q_out, 8)),
+                AB200_E_INVALID, "sum_lstm_cell: fp8 state output needs bf16 states and a scale buffer");
   const int vn = 16 / dtype_bytes(dtype);
   AB200_REQUIRE(D % vn == 0 && gates_row_stride % vn == 0, AB200_E_INVALID,
                 "sum_lstm_cell: D and the gate row stride must be multiples of %d", vn);
@@ -317,7 +348,7 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
 #define AB200_ARGS                                                                               \
   gates, gates_row_stride, emb_table, tokens, packed_argmax, cell_prev, cell_ln_weight,          \
       cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, \
-      clear_packed, clear_counter, s
+      clear_packed, clear_counter, state_q_out, state_scale_out, s
   switch (dtype) {
     case AB200_F32: return launch_cell<float, false>(AB200_ARGS);
     case AB200_BF16:

@@ -50,7 +50,7 @@ __global__ void unpack_steps_kernel(const unsigned long long* __restrict__ packe
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  size_t x0, gates, state[2], cell, packed, counters, logits, total;
+  size_t x0, gates, state[2], cell, packed, counters, state_q, state_scale, logits, total;
 };
 
 static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
@@ -69,6 +69,8 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
   w.cell = take(static_cast<size_t>(B) * sp->inner_dim * e);
   w.packed = take(static_cast<size_t>(B) * S * sizeof(uint64_t));
   w.counters = take(static_cast<size_t>(S) * sizeof(uint32_t));
+  w.state_q = take(static_cast<size_t>(B) * sp->inner_dim);
+  w.state_scale = take(static_cast<size_t>(B) * sizeof(float));
   w.logits = take(sp->dtype == AB200_F32 ? static_cast<size_t>(B) * sp->vocab * sizeof(float) : 0);
   w.total = off;
   return w;
@@ -79,7 +81,7 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
 using namespace ab200;
 
 extern "C" const char* ab200_last_error(void) { return g_err; }
-extern "C" int32_t ab200_abi_version(void) { return 2; }
+extern "C" int32_t ab200_abi_version(void) { return 3; }
 extern "C" int64_t ab200_launch_count(void) { return g_launches; }
 extern "C" int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches) {
   g_trace_base = reinterpret_cast<unsigned long long*>(device_slots);
@@ -126,6 +128,11 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
   // bf16, B <= 512: the cell kernel resets the arg-max slot / counter of its step and the head
   // kernel's last CTA writes the int64 tokens -> no memset node, no unpack launch.
   const bool fused_tokens = sp->dtype == AB200_BF16 && B <= 512;
+  // reference selection rule (arctic_speculator.py:726-727): quantised head iff batch <= 32
+  const bool fp8_head = sp->dtype == AB200_BF16 && sp->head_q != nullptr && sp->head_scale != nullptr &&
+                        B <= sp->fp8_head_max_batch && D % 16 == 0;
+  void* state_q = fp8_head ? ws + w.state_q : nullptr;
+  float* state_scale = fp8_head ? reinterpret_cast<float*>(ws + w.state_scale) : nullptr;
   if (!fused_tokens)
     AB200_CUDA_OK(cudaMemsetAsync(packed, 0, static_cast<size_t>(B) * num_steps * sizeof(uint64_t), s));
 
@@ -154,13 +161,18 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
                              state, cell, B, D, sp->vocab, sp->alpha, sp->eps, sp->dtype,
                              sp->emulate_eager_rounding,
                              fused_tokens ? packed + static_cast<size_t>(step) * B : nullptr,
-                             fused_tokens ? counters + step : nullptr, stream);
+                             fused_tokens ? counters + step : nullptr, state_q, state_scale, stream);
     if (rc != AB200_OK) return rc;
-    rc = ab200_head_argmax(state, sp->head, B, sp->head_rows, D, sp->vocab, D, D,
-                           packed + static_cast<size_t>(step) * B,
-                           fused_tokens ? tokens_out + step : nullptr, num_steps,
-                           fused_tokens ? counters + step : nullptr, sp->dtype, ws + w.logits,
-                           w.total - w.logits, stream);
+    if (fp8_head)
+      rc = ab200_head_argmax_fp8(state_q, state_scale, sp->head_q, sp->head_scale, B, sp->head_rows, D,
+                                 sp->vocab, D, D, packed + static_cast<size_t>(step) * B,
+                                 tokens_out + step, num_steps, counters + step, stream);
+    else
+      rc = ab200_head_argmax(state, sp->head, B, sp->head_rows, D, sp->vocab, D, D,
+                             packed + static_cast<size_t>(step) * B,
+                             fused_tokens ? tokens_out + step : nullptr, num_steps,
+                             fused_tokens ? counters + step : nullptr, sp->dtype, ws + w.logits,
+                             w.total - w.logits, stream);
     if (rc != AB200_OK) return rc;
     xin = state;
     ldx = D;

@@ -58,7 +58,8 @@ class ArcticLSTMSpeculator:
                  num_lookahead_tokens: Optional[int] = None, max_num_seqs: int = 256,
                  dtype: torch.dtype = torch.bfloat16, device: str | torch.device = "cuda",
                  scale_input: bool = True, enforce_eager: bool = False,
-                 emulate_eager_rounding: bool = True, alpha_flavor: str = "cuda") -> None:
+                 emulate_eager_rounding: bool = True, alpha_flavor: str = "cuda",
+                 quantize_lm_head: bool = False, fp8_head_max_batch: int = 32) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
         if dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("dtype must be torch.bfloat16 or torch.float32")
@@ -89,6 +90,13 @@ class ArcticLSTMSpeculator:
             raise ValueError("alpha_flavor must be 'cuda' or 'cpu'")
         self.alpha = float(alpha)
         self.eps = 1e-6
+        # FP8 duplicate of the head, used iff the (padded) batch <= 32 - the reference's `qhead`
+        # (arctic_speculator.py:436, 455-465, 726-727).  Off by default here: its parity is pinned
+        # to vLLM 0.22's fp8 ops, not to the reference's vLLM 0.9.2 binary.
+        self.quantize_lm_head = bool(quantize_lm_head) and dtype == torch.bfloat16 and inner_dim % 16 == 0
+        self.fp8_head_max_batch = fp8_head_max_batch
+        self._head_q: Optional[torch.Tensor] = None
+        self._head_scale: Optional[torch.Tensor] = None
 
         D, H, V = inner_dim, input_hidden_dim, vocab_size
         Vp = pad_vocab_size(V)
@@ -146,6 +154,21 @@ class ArcticLSTMSpeculator:
             if name in self._params:
                 self._set_param(name, w.to(device=self.device, dtype=self.dtype))
         self._desc = None
+        if self.quantize_lm_head:
+            self._quantize_head()
+
+    def _quantize_head(self) -> None:
+        """process_weights_after_loading of the reference's qhead (fp8.py:207-221): dynamic
+        per-tensor e4m3 quantisation of the (padded) head weight."""
+        head = self._params["head.0.weight"]
+        self._head_q = torch.empty(head.shape, dtype=torch.uint8, device=self.device)
+        self._head_scale = torch.zeros(1, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(self._lib.ab200_fp8_quantize_weight(
+                head.data_ptr(), self._head_q.data_ptr(), self._head_scale.data_ptr(), head.shape[0],
+                head.shape[1], head.stride(0), self._head_q.stride(0),
+                _capi.current_stream_ptr(self.device)), "ab200_fp8_quantize_weight")
+        self._desc = None
 
     # ---- native descriptor / workspace -------------------------------------------------------
     def _descriptor(self) -> _capi.LstmSpeculatorDesc:
@@ -169,6 +192,9 @@ class ArcticLSTMSpeculator:
             d.state_ln_w = p["state_ln.0.weight"].data_ptr()
             d.state_ln_b = p["state_ln.0.bias"].data_ptr()
             d.head = p["head.0.weight"].data_ptr()
+            d.head_q = self._head_q.data_ptr() if self._head_q is not None else None
+            d.head_scale = self._head_scale.data_ptr() if self._head_scale is not None else None
+            d.fp8_head_max_batch = self.fp8_head_max_batch if self._head_q is not None else 0
             self._desc = d
         return self._desc
 
@@ -237,7 +263,7 @@ class ArcticLSTMSpeculator:
                 p["cell_ln.0.weight"].data_ptr(), p["cell_ln.0.bias"].data_ptr(),
                 p["state_ln.0.weight"].data_ptr(), p["state_ln.0.bias"].data_ptr(),
                 state.data_ptr(), cell.data_ptr(), B, D, self.vocab_size, self.alpha, self.eps,
-                code, emu, None, None, stream), "ab200_sum_lstm_cell")
+                code, emu, None, None, None, None, stream), "ab200_sum_lstm_cell")
         return state.unsqueeze(1), cell.unsqueeze(1)
 
     def greedy_tokens(self, states: torch.Tensor) -> torch.Tensor:

@@ -233,7 +233,7 @@ def time_kernels_in_sequence(model, ids, hid, iters: int):
                 packed[s - 1].data_ptr() if s else None, cell.data_ptr(), p["cell_ln.0.weight"].data_ptr(),
                 p["cell_ln.0.bias"].data_ptr(), p["state_ln.0.weight"].data_ptr(),
                 p["state_ln.0.bias"].data_ptr(), state.data_ptr(), cell.data_ptr(), B, D, V, model.alpha,
-                1e-6, code, 1, packed[s].data_ptr(), counters[s:].data_ptr(), st))
+                1e-6, code, 1, packed[s].data_ptr(), counters[s:].data_ptr(), None, None, st))
             timed("head_argmax", lambda: lib.ab200_head_argmax(
                 state.data_ptr(), p["head.0.weight"].data_ptr(), B, p["head.0.weight"].shape[0], D, V, D, D,
                 packed[s].data_ptr(), toks[s].data_ptr(), 1, counters[s:].data_ptr(), code, None, 0, st))

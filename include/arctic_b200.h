@@ -114,6 +114,8 @@ AB200_API int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t 
  *   ln vectors [D]; outputs state_out, cell_out [B, D] (cell_out may alias cell_prev).
  *   clear_packed [B] / clear_counter [1] (optional): zeroed by this kernel so that the head
  *   kernel that follows finds its arg-max slot and completion counter reset (no memset node).
+ *   state_q_out [B, D] e4m3 / state_scale_out [B] f32 (optional, bf16 only): dynamic per-token
+ *   FP8 copy of the new state for the quantised head (see ab200_head_argmax_fp8).
  * D must be a multiple of 8 (16-byte vectors). */
 AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
                             const void* emb_table, const int64_t* tokens,
@@ -125,7 +127,8 @@ AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_strid
                             int64_t B, int64_t D, int64_t vocab,
                             float alpha, float eps, int32_t dtype,
                             int32_t emulate_eager_rounding,
-                            uint64_t* clear_packed, uint32_t* clear_counter, void* stream);
+                            uint64_t* clear_packed, uint32_t* clear_counter,
+                            void* state_q_out, float* state_scale_out, void* stream);
 
 /* out[M, N] = x[M, K] @ w[N, K]^T  (nn.Linear without bias).
  * Replaces: self.projs[i](prev_state), arctic_speculator.py:555-561,668 (cuBLAS in the reference).
@@ -158,6 +161,35 @@ AB200_API int32_t ab200_head_argmax(const void* x, const void* w,
                           int64_t* tokens_out, int64_t tokens_stride, uint32_t* done_counter,
                           int32_t dtype,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FP8 (e4m3) quantised head - SURVEY 8f "next" rank 1.
+ * Replaces: the reference's `qhead` used when the padded batch is <= 32
+ * (arctic_speculator.py:455-465, 726-727) = vLLM Fp8LinearMethod on an unquantised checkpoint
+ * (arctic_inference/vllm/spec_dec/fp8.py:207-221 weight quantisation, :276-308 apply):
+ *   weights     s_w = amax|W| / 448 (one scale),  q = sat_e4m3(w * (1/s_w))
+ *   activations s_x[row] = max(amax|x_row| / 448, 1/(448*512)),  q = sat_e4m3(x / s_x)
+ *   output      bf16( s_x[row] * (s_w * acc_fp32) )
+ * The arithmetic is pinned against vLLM's own ops (scaled_fp8_quant, cutlass_scaled_mm) run on a
+ * B200 (tests/test_fp8_gpu.py); vLLM 0.9.2 itself is absent, so parity with the reference's exact
+ * binary is unpinned.
+ */
+AB200_API int32_t ab200_fp8_quantize_weight(const void* w /*bf16 [rows,K]*/, void* q_out /*e4m3 [rows,K]*/,
+                                            float* scale_out /*[1]*/, int64_t rows, int64_t K,
+                                            int64_t ldw, int64_t ldq, void* stream);
+AB200_API int32_t ab200_fp8_quantize_rows(const void* x /*bf16 [M,K]*/, void* q_out /*e4m3 [M,K]*/,
+                                          float* scales_out /*[M]*/, int64_t M, int64_t K,
+                                          int64_t ldx, int64_t ldq, void* stream);
+/* out[M,N] (bf16) = dequantised xq[M,K] @ wq[N,K]^T; tcgen05.mma kind::f8f6f4. K % 16 == 0. */
+AB200_API int32_t ab200_linear_fp8(const void* xq, const float* x_scales, const void* wq,
+                                   const float* w_scale, void* out, int64_t M, int64_t N, int64_t K,
+                                   int64_t ldx, int64_t ldw, int64_t ldo, void* stream);
+/* Fused FP8 head + arg-max; arguments as ab200_head_argmax. */
+AB200_API int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, const void* wq,
+                                        const float* w_scale, int64_t M, int64_t w_rows, int64_t K,
+                                        int64_t vocab, int64_t ldx, int64_t ldw, uint64_t* packed_out,
+                                        int64_t* tokens_out, int64_t tokens_stride,
+                                        uint32_t* done_counter, void* stream);
 
 /* tokens_out[i * out_stride] = 0xFFFFFFFF - low32(packed[i])  for i < count (int64 output). */
 AB200_API int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
@@ -199,6 +231,10 @@ typedef struct ab200_lstm_speculator {
   const void* cell_ln_w; const void* cell_ln_b;   /* [D] */
   const void* state_ln_w; const void* state_ln_b; /* [D] */
   const void* head;         /* [head_rows, D] head.0.weight (tied across steps) */
+  /* optional FP8 head (reference: qhead, used iff the padded batch <= fp8_head_max_batch = 32) */
+  const void* head_q;       /* [head_rows, D] e4m3, or NULL */
+  const float* head_scale;  /* [1] */
+  int32_t fp8_head_max_batch;
 } ab200_lstm_speculator;
 
 AB200_API size_t ab200_lstm_workspace_bytes(const ab200_lstm_speculator* spec, int64_t B, int32_t num_steps);

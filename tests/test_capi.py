@@ -38,14 +38,14 @@ def test_ctypes_table_matches_header(built_lib):
     from arcticinference_b200 import _capi
     assert sorted(_capi.SIGNATURES) == _header_symbols()
     lib = _capi.lib()
-    assert lib.ab200_abi_version() == 2
+    assert lib.ab200_abi_version() == 3
     assert lib.ab200_last_error() == b""
 
 
 def test_descriptor_struct_layout():
-    """ctypes mirror of struct ab200_lstm_speculator: 4+4+8*4+4+4+4(+4 pad)+8*8 bytes."""
+    """ctypes mirror of struct ab200_lstm_speculator: 4+4+8*4+4+4+4(+4 pad)+8*8 + 8+8+4(+4 pad)."""
     from arcticinference_b200 import _capi
-    assert ctypes.sizeof(_capi.LstmSpeculatorDesc) == 120
+    assert ctypes.sizeof(_capi.LstmSpeculatorDesc) == 144
     assert _capi.LstmSpeculatorDesc.forget_emb.offset == 56
 
 

@@ -87,7 +87,7 @@ def test_fused_cell_against_oracle(capi, B, D, V, dtype):
         gates.data_ptr(), 4 * D, w["forget_emb.0.weight"].data_ptr(), tok.data_ptr(), None,
         cprev.data_ptr(), w["cell_ln.0.weight"].data_ptr(), w["cell_ln.0.bias"].data_ptr(),
         w["state_ln.0.weight"].data_ptr(), w["state_ln.0.bias"].data_ptr(), state.data_ptr(),
-        cell.data_ptr(), B, D, V, alpha, 1e-6, capi.torch_dtype_code(dtype), 1, None, None, stream()))
+        cell.data_ptr(), B, D, V, alpha, 1e-6, capi.torch_dtype_code(dtype), 1, None, None, None, None, stream()))
     if dtype == torch.bfloat16:
         assert relerr(state, s_ref.squeeze(1)) < BF16_STATE_TOL
         assert relerr(cell, c_ref.squeeze(1)) < BF16_STATE_TOL
@@ -114,7 +114,7 @@ def test_fused_cell_without_emulation_stays_in_tolerance(capi):
         w["cell_ln.0.weight"].data_ptr(), w["cell_ln.0.bias"].data_ptr(),
         w["state_ln.0.weight"].data_ptr(), w["state_ln.0.bias"].data_ptr(), state.data_ptr(),
         cell.data_ptr(), B, D, V, O.emulated_alpha(3, D, torch.bfloat16, "cuda"), 1e-6,
-        capi.AB200_BF16, 0, None, None, stream()))
+        capi.AB200_BF16, 0, None, None, None, None, stream()))
     assert relerr(state, s_ref.squeeze(1)) < BF16_STATE_TOL
     assert relerr(cell, c_ref.squeeze(1)) < BF16_STATE_TOL
 
