@@ -36,6 +36,9 @@ SIGNATURES = {
     "ab200_abi_version": (c_int32, []),
     "ab200_launch_count": (c_int64, []),
     "ab200_set_trace_buffer": (c_int32, [c_void_p, c_int32]),
+    "ab200_debug_cell_generic": (c_int32, [c_int32]),
+    "ab200_debug_unary_bf16": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int64, c_void_p]),
     "ab200_kv_write_bulk": (c_int32, [c_void_p, c_void_p, c_int64, c_int64,
                                       POINTER(c_void_p), POINTER(c_void_p),
                                       POINTER(c_void_p), POINTER(c_void_p), c_int32,

@@ -165,6 +165,18 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return r;
 }
 
+// Block-wide sum with ONE barrier: every warp reduces the per-warp partials itself (same xor tree,
+// same operands as block_sum's warp 0 -> bit-identical result).  `scratch` (>= 32 floats) must not
+// be reused before the next barrier of the caller; use a different buffer for back-to-back sums.
+__device__ __forceinline__ float block_sum_1sync(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  return warp_sum(lane < nwarps ? scratch[lane] : 0.f);
+}
+
 // Block-wide max of non-negative values, broadcast. `scratch` holds >= 33 floats.
 __device__ __forceinline__ float block_max(float v, float* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -13,6 +13,10 @@
 //
 // Roofline: HBM bytes per row = e * D * (4 gates + 1 emb row + 1 c_prev + 2 outputs); at the
 // BASELINE batch sizes (64..512 rows) the kernel is launch-latency bound.
+#include <cstdlib>
+#include <type_traits>
+
+#include "bf16_exact.cuh"
 #include "common.cuh"
 
 namespace ab200 {
@@ -215,6 +219,211 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
   if (threadIdx.x == 0) trace_stamp(trace, 2);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// bf16 + eager-rounding emulation, the production configuration: same results as
+// sum_lstm_cell_kernel<__nv_bfloat16, true, ITEMS> bit for bit (tests/test_cell_gpu.py), at about
+// a third of the instructions - see bf16_exact.cuh for why each shortcut is exact.  Values that
+// live across the two row reductions are kept as packed bf16x2 (they ARE bf16 in eager mode).
+// ------------------------------------------------------------------------------------------
+// per-device copy of the GELU table of bf16_exact.cuh (1 KB, L2-resident)
+__device__ float g_gelu_lut[kGeluLutSize];
+__global__ void gelu_lut_init_kernel() { g_gelu_lut[threadIdx.x] = gelu_lut_entry(threadIdx.x); }
+
+// FULL: D == 8 * ITEMS * blockDim.x (no ragged tail: bounds checks and zero-fills compile away)
+template <int ITEMS, int MAXT, int MINB, bool FULL, bool GUARD>
+__global__ void __launch_bounds__(MAXT, MINB)
+sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg,
+                            const __nv_bfloat16* __restrict__ emb,
+                            const int64_t* __restrict__ tokens,
+                            const unsigned long long* __restrict__ packed,
+                            const __nv_bfloat16* cell_prev,  // may alias cell_out
+                            const __nv_bfloat16* __restrict__ wc, const __nv_bfloat16* __restrict__ bc,
+                            const __nv_bfloat16* __restrict__ ws, const __nv_bfloat16* __restrict__ bs,
+                            __nv_bfloat16* __restrict__ state_out, __nv_bfloat16* cell_out, int32_t D,
+                            int64_t vocab, float alpha, float eps, float inv_d,
+                            unsigned long long* __restrict__ clear_packed,
+                            unsigned int* __restrict__ clear_counter, unsigned long long* trace,
+                            uint8_t* __restrict__ state_q, float* __restrict__ state_scale) {
+  using T = __nv_bfloat16;
+  __shared__ float scratch[33], scratch2[32];
+  __shared__ float gelu_lut[kGeluLutSize];
+  const int64_t row = blockIdx.x;
+  const int nvec = D / 8;
+
+  if (threadIdx.x == 0) trace_stamp(trace, 0);
+  pdl_launch_dependents();
+  if constexpr (GUARD) gelu_lut_fill(gelu_lut, g_gelu_lut);   // independent of the previous kernel
+  uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_lut));
+  asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));   // opaque: keep it in a register, do not rematerialise
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    trace_stamp(trace, 1);
+    if (clear_packed) clear_packed[row] = 0ull;
+    if (clear_counter && row == 0) *clear_counter = 0u;
+  }
+  int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
+  if (static_cast<uint64_t>(tok) >= static_cast<uint64_t>(vocab)) tok = tok < 0 ? 0 : vocab - 1;
+
+  const T* g = gates + row * ldg;
+  const T* z = emb + tok * static_cast<int64_t>(D);
+
+  uint32_t F[ITEMS][4], I[ITEMS][4], O[ITEMS][4], CC[ITEMS][4], C[ITEMS][4];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int vi = threadIdx.x + it * blockDim.x;
+    if (FULL || vi < nvec) {
+      const uint4 gf = ld_stream_16(g + 0 * D + vi * 8);
+      const uint4 gi = ld_stream_16(g + 1 * D + vi * 8);
+      const uint4 go = ld_stream_16(g + 2 * D + vi * 8);
+      const uint4 gc = ld_stream_16(g + 3 * D + vi * 8);
+      const uint4 ze = *reinterpret_cast<const uint4*>(z + vi * 8);
+      uint4 cp = make_uint4(0u, 0u, 0u, 0u);
+      if (cell_prev) cp = *reinterpret_cast<const uint4*>(cell_prev + row * D + vi * 8);
+      const uint32_t gfa[4] = {gf.x, gf.y, gf.z, gf.w}, gia[4] = {gi.x, gi.y, gi.z, gi.w};
+      const uint32_t goa[4] = {go.x, go.y, go.z, go.w}, gca[4] = {gc.x, gc.y, gc.z, gc.w};
+      const uint32_t zea[4] = {ze.x, ze.y, ze.z, ze.w}, cpa[4] = {cp.x, cp.y, cp.z, cp.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const f2 zz = unpack2(zea[p]), al = bcast2(alpha);
+        // torch.add(states, z.repeat(1,1,4), alpha): one rounding of fma(alpha, z, s)
+        const f2 sf = fma2(al, zz, unpack2(gfa[p])), si = fma2(al, zz, unpack2(gia[p]));
+        const f2 so = fma2(al, zz, unpack2(goa[p])), sc = fma2(al, zz, unpack2(gca[p]));
+        const uint32_t af = pack_rn(sf.a, sf.b), ai = pack_rn(si.a, si.b), ao = pack_rn(so.a, so.b);
+        CC[it][p] = pack_rn(sc.a, sc.b);
+        sigmoid6_bf16_exact<GUARD>(af, ai, ao, F[it][p], I[it][p], O[it][p]);
+        C[it][p] = cpa[p];
+        const uint32_t sq = mul2(CC[it][p], CC[it][p]);
+        ss += bf_lo(sq);
+        ss += bf_hi(sq);
+      }
+    } else if constexpr (!FULL) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) F[it][p] = I[it][p] = O[it][p] = CC[it][p] = C[it][p] = 0u;
+    }
+  }
+  // cell_ln (RMS, affine) -> GELU -> * input gate ; c = c_prev * f + candidate
+  ss = block_sum_1sync(ss, scratch);   // also orders gelu_lut_fill before the first table read
+  {
+    const float mean = ST<T>::round(ss * inv_d);
+    const float inv = ST<T>::round(rsqrtf(ST<T>::round(mean + eps)));
+    const uint32_t inv2 = pack_rn(inv, inv);
+    ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (FULL || vi < nvec) {
+        const uint4 w = *reinterpret_cast<const uint4*>(wc + vi * 8);
+        const uint4 b = *reinterpret_cast<const uint4*>(bc + vi * 8);
+        const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          uint32_t y = mul2(CC[it][p], inv2);
+          y = mul2(wa[p], y);
+          y = add2(y, ba[p]);
+          y = gelu2_bf16_exact<GUARD>(y, lut_s);
+          y = mul2(y, I[it][p]);
+          uint32_t cn = mul2(C[it][p], F[it][p]);
+          cn = add2(cn, y);
+          C[it][p] = cn;
+          const uint32_t sq = mul2(cn, cn);
+          ss += bf_lo(sq);
+          ss += bf_hi(sq);
+        }
+      }
+    }
+  }
+  // state_ln (RMS, affine) -> GELU -> * output gate
+  ss = block_sum_1sync(ss, scratch2);
+  {
+    const float mean = ST<T>::round(ss * inv_d);
+    const float inv = ST<T>::round(rsqrtf(ST<T>::round(mean + eps)));
+    const uint32_t inv2 = pack_rn(inv, inv);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (FULL || vi < nvec) {
+        const uint4 w = *reinterpret_cast<const uint4*>(ws + vi * 8);
+        const uint4 b = *reinterpret_cast<const uint4*>(bs + vi * 8);
+        const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          uint32_t y = mul2(C[it][p], inv2);
+          y = mul2(wa[p], y);
+          y = add2(y, ba[p]);
+          y = gelu2_bf16_exact<GUARD>(y, lut_s);
+          F[it][p] = mul2(y, O[it][p]);   // the new state (F is dead: reuse its registers)
+        }
+        *reinterpret_cast<uint4*>(state_out + row * D + vi * 8) =
+            make_uint4(F[it][0], F[it][1], F[it][2], F[it][3]);
+        *reinterpret_cast<uint4*>(cell_out + row * D + vi * 8) =
+            make_uint4(C[it][0], C[it][1], C[it][2], C[it][3]);
+      }
+    }
+  }
+  if (state_q != nullptr) {
+    // dynamic per-token FP8 copy of the state for the quantised head (see the generic kernel)
+    float amax = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        amax = fmaxf(amax, fmaxf(fabsf(bf_lo(F[it][p])), fabsf(bf_hi(F[it][p]))));
+    __syncthreads();   // scratch is free again (block_sum_1sync leaves no trailing barrier)
+    amax = block_max(amax, scratch);
+    const float scale = fmaxf(amax / kFp8Max, kFp8MinScale);
+    if (threadIdx.x == 0) state_scale[row] = scale;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (FULL || vi < nvec) {
+        uint32_t q[2] = {0u, 0u};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t lo = to_e4m3(bf_lo(F[it][p]) / scale), hi = to_e4m3(bf_hi(F[it][p]) / scale);
+          q[p >> 1] |= (lo | (hi << 8)) << (16 * (p & 1));
+        }
+        *reinterpret_cast<uint2*>(state_q + row * D + vi * 8) = make_uint2(q[0], q[1]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) trace_stamp(trace, 2);
+}
+
+// bf16 unary functions of the bit-exact emulation on arbitrary inputs (test hook: all 65 536
+// values).  fast/exact: bf16 results of the shortcut / of ATen's formula; fast32/exact32
+// (optional): the unguarded fast approximation and ATen's value in fp32, to measure the guard.
+__global__ void unary_bf16_kernel(int op, const uint16_t* __restrict__ in, uint16_t* __restrict__ fast,
+                                  uint16_t* __restrict__ exact, float* __restrict__ fast32,
+                                  float* __restrict__ exact32, int64_t n) {
+  __shared__ float gelu_lut[kGeluLutSize];
+#pragma unroll 1
+  for (int i = threadIdx.x; i < kGeluLutSize; i += blockDim.x) gelu_lut[i] = gelu_lut_entry(i);
+  uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_lut));
+  asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));
+  __syncthreads();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x = __uint_as_float(static_cast<uint32_t>(in[i]) << 16);
+    const uint32_t x2 = static_cast<uint32_t>(in[i]) * 0x10001u;
+    uint32_t f, f_i, f_o;
+    if (op == 0) sigmoid6_bf16_exact<true>(x2, x2, x2, f, f_i, f_o);
+    else f = gelu2_bf16_exact<true>(x2, lut_s);
+    const float e = op == 0 ? sigmoid_aten(x) : gelu_erf_aten(x);
+    fast[i] = static_cast<uint16_t>(f & 0xFFFFu);
+    exact[i] = static_cast<uint16_t>(pack_rn(e, 0.f) & 0xFFFFu);
+    if (fast32) {
+      const f2 h = half_erfc2(f2{x, x});
+      fast32[i] = op == 0 ? sigmoid_fast(x) : gelu_lut_or(x * (x < 0.0f ? h.a : 1.0f - h.a), x, lut_s);
+    }
+    if (exact32) exact32[i] = e;
+  }
+}
+
+// debug switch (ab200_debug_cell_generic): 1 = run the generic kernel also for bf16 + emulation
+static int g_cell_generic = 0;
+
 // block size / items-per-thread for a row of `nvec` 16-byte vectors
 static bool row_launch_shape(int64_t nvec, int* threads, int* items) {
   for (int it : {1, 2, 4}) {
@@ -255,7 +464,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
                        const void* bc, const void* ws, const void* bs, void* state_out,
                        void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
                        uint64_t* clear_packed, uint32_t* clear_counter, void* state_q,
-                       float* state_scale, cudaStream_t s) {
+                       float* state_scale, bool guard, cudaStream_t s) {
   int threads, items;
   AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
                 "sum_lstm_cell: D %lld too large", (long long)D);
@@ -278,6 +487,56 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
 #define AB200_CELL_ARGS                                                                          \
   a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
       vocab, alpha, eps, a_clear, a_cnt, a_trace, a_sq, state_scale
+  if constexpr (EMU && std::is_same<T, __nv_bfloat16>::value) {
+    if (!g_cell_generic) {
+      // first use on this device: fill the GELU table; this one cell launch is then fully
+      // stream-serialised (no PDL) because the kernel reads the table before its dependency wait
+      static bool lut_ready[64] = {};
+      int dev = 0;
+      AB200_CUDA_OK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !lut_ready[dev]) {
+        gelu_lut_init_kernel<<<1, kGeluLutSize, 0, s>>>();
+        AB200_CHECK_LAUNCH("gelu_lut_init_kernel");
+        lc.cfg.numAttrs = 0;
+        if (dev >= 0 && dev < 64) lut_ready[dev] = true;
+      }
+      // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
+      // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
+      const float inv_d = 1.0f / static_cast<float>(D);
+      const bool full = D == 8LL * items * threads;
+#define AB200_FAST_ARGS                                                                          \
+  a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
+      vocab, alpha, eps, inv_d, a_clear, a_cnt, a_trace, a_sq, state_scale
+#define AB200_FAST_LAUNCH2(IT, MAXT, MINB, FULLV)                                                 \
+  do {                                                                                           \
+    if (guard)                                                                                   \
+      AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_bf16x2_kernel<IT, MAXT, MINB, FULLV, true>, \
+                                       AB200_FAST_ARGS));                                        \
+    else                                                                                         \
+      AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_bf16x2_kernel<IT, MAXT, MINB, FULLV, false>, \
+                                       AB200_FAST_ARGS));                                        \
+  } while (0)
+#define AB200_FAST_LAUNCH(IT, MAXT, MINB)                                                        \
+  do {                                                                                           \
+    if (full) AB200_FAST_LAUNCH2(IT, MAXT, MINB, true);                                          \
+    else AB200_FAST_LAUNCH2(IT, MAXT, MINB, false);                                              \
+  } while (0)
+      // 16 elements per thread amortise the per-thread prologue once the grid fills the GPU many
+      // times over; below that the shorter per-thread chain of 8 elements wins on latency
+      if (B >= 4096 && items == 1 && threads % 64 == 0 && threads >= 128 && threads <= 512) {
+        lc.cfg.blockDim = dim3(threads / 2);
+        AB200_FAST_LAUNCH(2, 256, 4);
+      } else if (items == 1 && threads <= 512) AB200_FAST_LAUNCH(1, 512, 3);
+      else if (items == 1) AB200_FAST_LAUNCH(1, 1024, 1);
+      else if (items == 2) AB200_FAST_LAUNCH(2, 1024, 1);
+      else AB200_FAST_LAUNCH(4, 1024, 1);
+#undef AB200_FAST_LAUNCH2
+#undef AB200_FAST_LAUNCH
+#undef AB200_FAST_ARGS
+      AB200_CHECK_LAUNCH("sum_lstm_cell_bf16x2_kernel");
+      return AB200_OK;
+    }
+  }
   switch (items) {
     case 1: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 1>, AB200_CELL_ARGS)); break;
     case 2: AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_kernel<T, EMU, 2>, AB200_CELL_ARGS)); break;
@@ -348,7 +607,7 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
 #define AB200_ARGS                                                                               \
   gates, gates_row_stride, emb_table, tokens, packed_argmax, cell_prev, cell_ln_weight,          \
       cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, \
-      clear_packed, clear_counter, state_q_out, state_scale_out, s
+      clear_packed, clear_counter, state_q_out, state_scale_out, emulate_eager_rounding != 2, s
   switch (dtype) {
     case AB200_F32: return launch_cell<float, false>(AB200_ARGS);
     case AB200_BF16:
@@ -359,4 +618,21 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
     default: AB200_REQUIRE(false, AB200_E_INVALID, "sum_lstm_cell: unsupported dtype %d", dtype);
   }
 #undef AB200_ARGS
+}
+
+extern "C" int32_t ab200_debug_cell_generic(int32_t on) {
+  const int32_t prev = g_cell_generic;
+  g_cell_generic = on != 0;
+  return prev;
+}
+
+extern "C" int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16_t* out_fast,
+                                          uint16_t* out_exact, float* out_fast32,
+                                          float* out_exact32, int64_t n, void* stream) {
+  AB200_REQUIRE((op == 0 || op == 1) && in && out_fast && out_exact && n > 0, AB200_E_INVALID,
+                "debug_unary_bf16: bad arguments");
+  unary_bf16_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(op, in, out_fast, out_exact,
+                                                                         out_fast32, out_exact32, n);
+  AB200_CHECK_LAUNCH("unary_bf16_kernel");
+  return AB200_OK;
 }

@@ -58,7 +58,7 @@ class ArcticLSTMSpeculator:
                  num_lookahead_tokens: Optional[int] = None, max_num_seqs: int = 256,
                  dtype: torch.dtype = torch.bfloat16, device: str | torch.device = "cuda",
                  scale_input: bool = True, enforce_eager: bool = False,
-                 emulate_eager_rounding: bool = True, alpha_flavor: str = "cuda",
+                 emulate_eager_rounding: bool | int = True, alpha_flavor: str = "cuda",
                  quantize_lm_head: bool = False, fp8_head_max_batch: int = 32) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
         if dtype not in (torch.bfloat16, torch.float32):
@@ -78,7 +78,11 @@ class ArcticLSTMSpeculator:
         self.tie_lstm_embs = True
         self.scale_input = scale_input
         self.method = "sum_lstm"
-        self.emulate_eager_rounding = bool(emulate_eager_rounding) and dtype != torch.float32
+        # 0 / False: fp32 internally; 1 / True: bit-exact eager emulation; 2: "faithful" (same rounding
+        # points, unguarded fast sigmoid / GELU) - include/arctic_b200.h, ab200_sum_lstm_cell
+        self.emulate_eager_rounding = 0 if dtype == torch.float32 else int(emulate_eager_rounding)
+        if self.emulate_eager_rounding not in (0, 1, 2):
+            raise ValueError("emulate_eager_rounding must be 0, 1 or 2")
         # arctic_speculator.py:575-577
         self.state_weight = 0.5 ** (0.5 / n_predict)
         self.emb_weight = math.sqrt((1 - self.state_weight ** 2) * (inner_dim / 2))

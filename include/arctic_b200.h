@@ -116,6 +116,11 @@ AB200_API int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t 
  *   kernel that follows finds its arg-max slot and completion counter reset (no memset node).
  *   state_q_out [B, D] e4m3 / state_scale_out [B] f32 (optional, bf16 only): dynamic per-token
  *   FP8 copy of the new state for the quantised head (see ab200_head_argmax_fp8).
+ *   emulate_eager_rounding (bf16 / f16 only): 0 = fp32 internally, one rounding at the end;
+ *   1 = every value PyTorch eager materialises is rounded to the storage dtype at that point and
+ *   sigmoid / erf-GELU round exactly as ATen's CUDA kernels do (bit-identical states);
+ *   2 (bf16) = the same rounding points with unguarded fast sigmoid / GELU ("faithful": about
+ *   0.1 % of the elements differ from mode 1 by one bf16 ulp) for the bandwidth-bound regime.
  * D must be a multiple of 8 (16-byte vectors). */
 AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
                             const void* emb_table, const int64_t* tokens,
@@ -209,6 +214,18 @@ AB200_API int32_t ab200_linear_simt_bf16(const void* x, const void* w, void* out
                                int64_t M, int64_t N, int64_t K,
                                int64_t ldx, int64_t ldw, int64_t ldo, void* stream);
 AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
+
+/* ---- test hooks (not on the product path) ------------------------------------------------
+ * ab200_debug_cell_generic(1): route bf16 + eager-rounding emulation through the generic
+ *   (instruction-heavy) cell kernel instead of the bf16x2 kernel; returns the previous setting.
+ *   The two must agree bit for bit (tests/test_cell_gpu.py).
+ * ab200_debug_unary_bf16: op 0 = sigmoid, 1 = erf-GELU on n bf16 bit patterns; out_fast is the
+ *   cell kernel's shortcut, out_exact ATen's formula (csrc/bf16_exact.cuh), both rounded to bf16;
+ *   out_fast32 / out_exact32: the unguarded approximation and ATen's value in fp32. */
+AB200_API int32_t ab200_debug_cell_generic(int32_t on);
+AB200_API int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16_t* out_fast,
+                                         uint16_t* out_exact, float* out_fast32 /*optional*/,
+                                         float* out_exact32 /*optional*/, int64_t n, void* stream);
 
 /* Whole draft loop: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + argmax) -> token unpack.
  * Replaces: ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751) as driven by

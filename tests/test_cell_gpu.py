@@ -1,0 +1,190 @@
+"""GPU: the bf16x2 fused-cell kernel (production: bf16 + eager-rounding emulation) is bit-identical
+to (i) PyTorch's own CUDA bf16 sigmoid / erf-GELU on ALL 65 536 bf16 inputs, (ii) the generic
+(instruction-heavy, ATen-formula) cell kernel on random and adversarial rows, (iii) the op-for-op
+oracle.  See arcticinference_b200/csrc/bf16_exact.cuh for the argument why the shortcuts are exact."""
+import pytest
+import torch
+
+from oracle import speculator_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from arcticinference_b200 import _capi
+    return _capi
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def all_bf16():
+    bits = torch.arange(65536, dtype=torch.int32, device=DEV).to(torch.int16)
+    return bits, bits.view(torch.bfloat16)
+
+
+def nan_equal_bits(a_bits, b_bits):
+    a, b = a_bits.view(torch.bfloat16), b_bits.view(torch.bfloat16)
+    both_nan = a.isnan() & b.isnan()
+    return (a_bits == b_bits) | both_nan
+
+
+@pytest.mark.parametrize("op,name", [(0, "sigmoid"), (1, "gelu")])
+def test_unary_shortcuts_exact_on_all_65536_inputs(capi, op, name):
+    bits, x = all_bf16()
+    fast = torch.empty_like(bits)
+    exact = torch.empty_like(bits)
+    f32 = torch.empty(65536, dtype=torch.float32, device=DEV)
+    e32 = torch.empty_like(f32)
+    capi.check(capi.lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
+                                                 f32.data_ptr(), e32.data_ptr(), 65536, st()))
+    torch.cuda.synchronize()
+    ref = (torch.sigmoid(x) if op == 0 else torch.nn.functional.gelu(x)).view(torch.int16)
+    ok_exact = nan_equal_bits(exact, ref)
+    assert ok_exact.all(), f"{name}: ATen-formula path differs from torch on {(~ok_exact).sum().item()} inputs"
+    # how much guard the unguarded approximation needs (fp32 ulps) in the domain the guard covers
+    xf = x.float()
+    dom = (xf >= -16) if op == 0 else (xf > -2)
+    dom &= torch.isfinite(xf) & torch.isfinite(e32) & (e32.abs() > 1e-30)
+    ulps = (f32.view(torch.int32)[dom].long() - e32.view(torch.int32)[dom].long()).abs()
+    print(f"{name}: max |fast - ATen| = {ulps.max().item()} fp32 ulps over {int(dom.sum())} inputs "
+          f"(99.9th pct {ulps.float().quantile(0.999).item():.0f})")
+    ok = nan_equal_bits(fast, ref)
+    bad = (~ok).nonzero().flatten()
+    assert ok.all(), (f"{name}: shortcut differs from torch on {bad.numel()} inputs, e.g. "
+                      f"{[(hex(bits[i].item() & 0xFFFF), x[i].item()) for i in bad[:8]]}")
+
+
+def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
+    B, D4 = gates.shape
+    D = D4 // 4
+    V = emb.shape[0]
+    lib = capi.lib()
+    state = torch.empty(B, D, device=DEV, dtype=torch.bfloat16)
+    cell = torch.empty_like(state)
+    sq = torch.empty(B, D, device=DEV, dtype=torch.uint8) if want_fp8 else None
+    ss = torch.empty(B, device=DEV, dtype=torch.float32) if want_fp8 else None
+    prev = lib.ab200_debug_cell_generic(1 if generic else 0)
+    try:
+        capi.check(lib.ab200_sum_lstm_cell(
+            gates.data_ptr(), gates.stride(0), emb.data_ptr(), tok.data_ptr(), None,
+            cprev.data_ptr() if cprev is not None else None, ln[0].data_ptr(), ln[1].data_ptr(),
+            ln[2].data_ptr(), ln[3].data_ptr(), state.data_ptr(), cell.data_ptr(), B, D, V, alpha, 1e-6,
+            capi.AB200_BF16, 1, None, None, sq.data_ptr() if want_fp8 else None,
+            ss.data_ptr() if want_fp8 else None, st()))
+        torch.cuda.synchronize()
+    finally:
+        lib.ab200_debug_cell_generic(prev)
+    return state, cell, sq, ss
+
+
+@pytest.mark.parametrize("B,D,gate_std,with_prev", [
+    (64, 4096, 1.3, True), (64, 4096, 1.3, False), (7, 2880, 1.0, True), (33, 8192, 2.0, True),
+    (16, 256, 6.0, True),        # saturated gates: |x| up to ~25
+    (5, 40, 1.0, True),          # D not a multiple of 64: ragged last warp
+    (3, 20000, 1.5, True),       # ITEMS = 4 path
+    (2048, 1024, 1.3, True),
+])
+def test_bf16x2_kernel_bit_identical_to_generic_kernel(capi, B, D, gate_std, with_prev):
+    torch.manual_seed(B * 131 + D)
+    V = 1000
+    gates = (torch.randn(B, 4 * D, device=DEV) * gate_std).to(torch.bfloat16)
+    emb = (torch.randn(V, D, device=DEV) * 0.02).to(torch.bfloat16)
+    tok = torch.randint(0, V, (B,), device=DEV)
+    cprev = (torch.randn(B, D, device=DEV) * 0.8).to(torch.bfloat16) if with_prev else None
+    ln = [(torch.randn(D, device=DEV) * 0.1 + (1.0 if i % 2 == 0 else 0.0)).to(torch.bfloat16) for i in range(4)]
+    alpha = 23.07
+    a = run_cell(capi, False, gates, emb, tok, cprev, ln, alpha, want_fp8=(D % 16 == 0))
+    b = run_cell(capi, True, gates, emb, tok, cprev, ln, alpha, want_fp8=(D % 16 == 0))
+    assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16)), "state differs"
+    assert torch.equal(a[1].view(torch.int16), b[1].view(torch.int16)), "cell differs"
+    if a[2] is not None:
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), "fp8 state copy differs"
+
+
+def test_bf16x2_kernel_adversarial_values(capi):
+    """Gate pre-activations that hit every special region: huge, tiny, zero, negative zero, the
+    GELU table range, values whose sigmoid / GELU sits next to a bf16 rounding tie."""
+    D, V = 4096, 16
+    vals = torch.tensor([0.0, -0.0, 1e-30, -1e-30, 1e30, -1e30, 17.0, -17.0, 88.0, -88.0, -2.0, -1.9921875,
+                         -7.96875, -8.0, -5.5, 3.0, 100.0, -100.0, 0.5, -0.5], device=DEV)
+    torch.manual_seed(0)
+    gates = vals[torch.randint(0, vals.numel(), (32, 4 * D), device=DEV)].to(torch.bfloat16)
+    gates[16:] = (torch.randn(16, 4 * D, device=DEV) * 3).to(torch.bfloat16)
+    emb = torch.zeros(V, D, device=DEV, dtype=torch.bfloat16)          # a = g exactly
+    tok = torch.zeros(32, dtype=torch.long, device=DEV)
+    cprev = vals[torch.randint(0, vals.numel(), (32, D), device=DEV)].clamp(-50, 50).to(torch.bfloat16)
+    # LN weights that sweep the GELU input over a wide range, incl. the (-8, -2] table
+    ln = [(torch.linspace(-6, 6, D, device=DEV)).to(torch.bfloat16), (torch.randn(D, device=DEV)).to(torch.bfloat16),
+          (torch.linspace(4, -9, D, device=DEV)).to(torch.bfloat16), (torch.randn(D, device=DEV) * 2).to(torch.bfloat16)]
+    a = run_cell(capi, False, gates, emb, tok, cprev, ln, 23.07)
+    b = run_cell(capi, True, gates, emb, tok, cprev, ln, 23.07)
+    eq = lambda x, y: bool(nan_equal_bits(x.view(torch.int16), y.view(torch.int16)).all())
+    assert eq(a[0], b[0]) and eq(a[1], b[1])
+
+
+def test_bf16x2_kernel_matches_op_for_op_oracle(capi):
+    """Teacher-forced single step against the ATen op sequence (CUDA eager) - states and cells."""
+    V, H, D, B = 5000, 4096, 4096, 64
+    w = O.make_weights(V, H, D, torch.bfloat16, seed=3, device=DEV)
+    ref = O.RefLSTMSpeculator(w, V, 3)
+    ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=4, device=DEV)
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=3, max_num_seqs=B, device=DEV)
+    m.load_weights(w.items())
+    cs = torch.zeros(B, 1, D, device=DEV, dtype=torch.bfloat16)
+    s_ref, c_ref = ref.generate_states(ids.unsqueeze(1), hid.unsqueeze(1), 0, cs)
+    s, c = m.generate_states(ids.unsqueeze(1), hid.unsqueeze(1), 0, cs)
+    assert (s.view(torch.int16) == s_ref.view(torch.int16)).float().mean().item() > 0.9995
+    assert (c.view(torch.int16) == c_ref.view(torch.int16)).float().mean().item() > 0.9995
+
+
+def test_faithful_mode_is_within_one_bf16_ulp_and_rare(capi):
+    """emulate_eager_rounding = 2: same rounding points, unguarded fast sigmoid / GELU.  Differences
+    from the exact mode must be rare and never exceed one bf16 ulp of the affected GATE / GELU value;
+    on the outputs we bound the fraction of differing elements and their relative size."""
+    B, D, V = 512, 4096, 1000
+    torch.manual_seed(11)
+    gates = (torch.randn(B, 4 * D, device=DEV) * 1.3).to(torch.bfloat16)
+    emb = (torch.randn(V, D, device=DEV) * 0.02).to(torch.bfloat16)
+    tok = torch.randint(0, V, (B,), device=DEV)
+    cprev = (torch.randn(B, D, device=DEV) * 0.8).to(torch.bfloat16)
+    ln = [(torch.randn(D, device=DEV) * 0.1 + (1.0 if i % 2 == 0 else 0.0)).to(torch.bfloat16) for i in range(4)]
+    lib = capi.lib()
+    outs = {}
+    for mode in (1, 2):
+        state = torch.empty(B, D, device=DEV, dtype=torch.bfloat16)
+        cell = torch.empty_like(state)
+        capi.check(lib.ab200_sum_lstm_cell(
+            gates.data_ptr(), gates.stride(0), emb.data_ptr(), tok.data_ptr(), None, cprev.data_ptr(),
+            ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr(), state.data_ptr(),
+            cell.data_ptr(), B, D, V, 23.07, 1e-6, capi.AB200_BF16, mode, None, None, None, None, st()))
+        torch.cuda.synchronize()
+        outs[mode] = (state, cell)
+    for name, a, b in (("state", outs[1][0], outs[2][0]), ("cell", outs[1][1], outs[2][1])):
+        diff = (a.view(torch.int16) != b.view(torch.int16))
+        frac = diff.float().mean().item()
+        rel = ((a.float() - b.float()).abs() / a.float().abs().clamp_min(1e-3)).max().item()
+        print(f"faithful vs exact, {name}: {frac:.5%} of elements differ, max relative difference {rel:.3e}")
+        assert frac < 0.01 and rel < 2.0 ** -6
+
+
+def test_faithful_mode_token_agreement():
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    V, H, D, S, B = 128256, 4096, 4096, 3, 64
+    w = O.make_weights(V, H, D, torch.bfloat16, seed=0, device=DEV)
+    ref = O.RefLSTMSpeculator(w, V, S)
+    m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B,
+                             device=DEV, emulate_eager_rounding=2)
+    m.load_weights(w.items())
+    agree = total = 0
+    for seed in range(24):
+        ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=700 + seed, device=DEV)
+        got, exp = m.generate_proposals(ids, hid, S), ref.generate_proposals(ids, hid, S)
+        agree += (got == exp).sum().item()
+        total += got.numel()
+    print(f"faithful mode: free-running draft-token agreement {agree / total:.5f} on {total} tokens")
+    assert agree / total >= 0.999
