@@ -60,6 +60,9 @@ bool pdl_enabled();
 // next_trace_slot() returns nullptr when tracing is off.
 unsigned long long* next_trace_slot();
 
+// rows of a batch that share one pass over the weights in the tcgen05 GEMMs (gemm_sm100.cu)
+int gemm_rows_per_pass();
+
 struct LaunchCfg {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];

@@ -167,7 +167,7 @@ constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB slot per m-tile (only b
 constexpr int kTmemCols = 512;                 // 2 accumulator buffers x MT m-tiles x (256 / MT) columns
 constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kMaxRowsPerPass = 512;           // MT <= 4 m-tiles share one weight stream
+constexpr int kMaxRowsPerPassLimit = 512;      // MT <= 4 m-tiles can share one weight stream
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // weights: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;   // activations: re-read by every tile
 
@@ -183,6 +183,7 @@ struct GemmParams {
   int32_t l2_prefetch_kb;  // extra W k-blocks prefetched into L2 before the dependency wait
   int32_t pre_stages;      // smem stages filled with W before the dependency wait
   int32_t late_trigger;    // 1: griddepcontrol.launch_dependents after the last TMA load
+  int32_t m64;             // 1: UMMA M = 64 (MT == 1, <= 64 rows): row r lives in TMEM lane (r/16)*32 + r%16
   uint32_t tx_bytes;    // bytes landing per stage
   uint32_t idesc;
   __nv_bfloat16* out;   // EPI_STORE
@@ -345,6 +346,11 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     // with L2 atomics only, so these warps sleep in mbarrier.try_wait instead of sitting in
     // griddepcontrol.wait next to the (issue-bound) cell kernel that shares the SM.
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    // batch row of this thread inside m-tile 0 (M = 128: lane = row; M = 64: 16 rows per quadrant)
+    const bool m64 = MT == 1 && p.m64 != 0;
+    const int row_in_tile = m64 ? quad * 16 + lane : quad * 32 + lane;
+    const bool lane_used = !m64 || lane < 16;
+    const int warp_row0 = m64 ? quad * 16 : quad * 32;
     float best[MT];
     uint32_t best_idx[MT];
 #pragma unroll
@@ -363,17 +369,17 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
           sb = __ldcg(p.w_scale);
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
-            const int r = t * kTileM + quad * 32 + lane;
-            sa[t] = r < p.m_rows ? __ldcg(p.x_scales + r) : 0.f;
+            const int r = t * kTileM + row_in_tile;
+            sa[t] = (lane_used && r < p.m_rows) ? __ldcg(p.x_scales + r) : 0.f;
           }
         }
       }
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        const int row = t * kTileM + quad * 32 + lane;   // batch row inside the pass
-        const bool row_ok = row < p.m_rows;
+        const int row = t * kTileM + row_in_tile;   // batch row inside the pass
+        const bool row_ok = lane_used && row < p.m_rows;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * MT + t) * kAccSlot;
-        if (t * kTileM + quad * 32 >= p.m_rows) continue;  // whole warp out of range (warp-uniform)
+        if (t * kTileM + warp_row0 >= p.m_rows) continue;  // whole warp out of range (warp-uniform)
         for (int c0 = 0; c0 < p.block_n; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
@@ -424,8 +430,9 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     if constexpr (EPI == EPI_ARGMAX) {
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        const int row = t * kTileM + quad * 32 + lane;
-        if (row < p.m_rows && best_idx[t] != 0xFFFFFFFFu) atomicMax(p.packed + row, pack_arg(best[t], best_idx[t]));
+        const int row = t * kTileM + row_in_tile;
+        if (lane_used && row < p.m_rows && best_idx[t] != 0xFFFFFFFFu)
+          atomicMax(p.packed + row, pack_arg(best[t], best_idx[t]));
       }
       if (p.tokens_out != nullptr) {
         // The last CTA to finish turns the packed maxima into int64 token ids (folds the
@@ -531,6 +538,20 @@ int pick_block_n(int64_t N, int sms, int max_bn) {
   return best_bn;
 }
 
+static int env_int(const char* name, int dflt);
+}  // namespace ab200
+// Rows that share one pass over the weights.  256 (MT <= 2, block_n <= 128) by default: at 512
+// rows the MT = 4 variant is left with 64-column tiles and becomes bound by the L2 -> SM ingest
+// of the activation tiles (measured 568 us vs 2 x 222 us for the 8B head); AB200_ROWS_PER_PASS=512
+// re-enables it.
+int ab200::gemm_rows_per_pass() {
+  static const int v = [] {
+    const int e = env_int("AB200_ROWS_PER_PASS", 256);
+    return e >= 512 ? 512 : (e >= 256 ? 256 : 128);
+  }();
+  return v;
+}
+namespace ab200 {
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -588,8 +609,10 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   // instruction descriptor: D=f32 [4,6), A/B format [7,10)/[10,13) (kind::f16: 1 = bf16;
   // kind::f8f6f4: 0 = e4m3), K-major A/B, N>>3 [17,23), M>>4 [24,29)
   const uint32_t fmt = KIND == KIND_BF16 ? 1u : 0u;
+  // <= 64 rows: UMMA M = 64 halves the tensor-pipe work (and power) of this HBM-bound kernel
+  p.m64 = (MT == 1 && m_rows <= 64 && env_int("AB200_UMMA_M64", 1)) ? 1 : 0;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
-            (static_cast<uint32_t>(kTileM >> 4) << 24);
+            (static_cast<uint32_t>((p.m64 ? 64 : kTileM) >> 4) << 24);
   p.x_scales = ax.x_scales;
   p.w_scale = ax.w_scale;
   p.out = out;
@@ -621,11 +644,11 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
   AB200_REQUIRE(M > 0 && w_rows > 0 && K > 0 && n_valid > 0 && n_valid <= w_rows &&
                     w_rows < (1LL << 31) && K < (1LL << 31),
                 AB200_E_INVALID, "bf16 GEMM: bad sizes");
-  AB200_REQUIRE(ax.tokens_out == nullptr || (M <= kMaxRowsPerPass && ax.done_counter != nullptr),
+  AB200_REQUIRE(ax.tokens_out == nullptr || (M <= gemm_rows_per_pass() && ax.done_counter != nullptr),
                 AB200_E_INVALID, "head_argmax: fused token output needs M <= %d and a done counter",
-                kMaxRowsPerPass);
-  for (int64_t m0 = 0; m0 < M; m0 += kMaxRowsPerPass) {
-    const int64_t rows = M - m0 < kMaxRowsPerPass ? M - m0 : kMaxRowsPerPass;
+                gemm_rows_per_pass());
+  for (int64_t m0 = 0; m0 < M; m0 += gemm_rows_per_pass()) {
+    const int64_t rows = M - m0 < gemm_rows_per_pass() ? M - m0 : gemm_rows_per_pass();
     const char* xp = static_cast<const char*>(x) + m0 * ldx * esize;
     __nv_bfloat16* op = out ? out + m0 * ldo : nullptr;
     ArgmaxExtra a = ax;
@@ -797,7 +820,7 @@ extern "C" int32_t ab200_head_argmax(const void* x, const void* w, int64_t M, in
   AB200_REQUIRE(dtype == AB200_BF16, AB200_E_INVALID, "head_argmax: dtype must be bf16 or f32");
   ArgmaxExtra ax;
   ax.packed = reinterpret_cast<unsigned long long*>(packed_out);
-  if (tokens_out != nullptr && M <= kMaxRowsPerPass && done_counter != nullptr) {
+  if (tokens_out != nullptr && M <= gemm_rows_per_pass() && done_counter != nullptr) {
     ax.tokens_out = tokens_out;
     ax.tokens_stride = tokens_stride;
     ax.done_counter = done_counter;
@@ -839,7 +862,7 @@ extern "C" int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, 
   ax.packed = reinterpret_cast<unsigned long long*>(packed_out);
   ax.x_scales = x_scales;
   ax.w_scale = w_scale;
-  if (tokens_out != nullptr && M <= kMaxRowsPerPass && done_counter != nullptr) {
+  if (tokens_out != nullptr && M <= gemm_rows_per_pass() && done_counter != nullptr) {
     ax.tokens_out = tokens_out;
     ax.tokens_stride = tokens_stride;
     ax.done_counter = done_counter;

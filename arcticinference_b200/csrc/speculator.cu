@@ -125,9 +125,9 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
   uint64_t* packed = reinterpret_cast<uint64_t*>(ws + w.packed);
 
   uint32_t* counters = reinterpret_cast<uint32_t*>(ws + w.counters);
-  // bf16, B <= 512: the cell kernel resets the arg-max slot / counter of its step and the head
+  // bf16, B <= rows per GEMM pass (256): the cell kernel resets the arg-max slot / counter of its step and the head
   // kernel's last CTA writes the int64 tokens -> no memset node, no unpack launch.
-  const bool fused_tokens = sp->dtype == AB200_BF16 && B <= 512;
+  const bool fused_tokens = sp->dtype == AB200_BF16 && B <= gemm_rows_per_pass();
   // reference selection rule (arctic_speculator.py:726-727): quantised head iff batch <= 32
   const bool fp8_head = sp->dtype == AB200_BF16 && sp->head_q != nullptr && sp->head_scale != nullptr &&
                         B <= sp->fp8_head_max_batch && D % 16 == 0;
@@ -166,7 +166,8 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
     if (fp8_head)
       rc = ab200_head_argmax_fp8(state_q, state_scale, sp->head_q, sp->head_scale, B, sp->head_rows, D,
                                  sp->vocab, D, D, packed + static_cast<size_t>(step) * B,
-                                 tokens_out + step, num_steps, counters + step, stream);
+                                 fused_tokens ? tokens_out + step : nullptr, num_steps,
+                                 fused_tokens ? counters + step : nullptr, stream);
     else
       rc = ab200_head_argmax(state, sp->head, B, sp->head_rows, D, sp->vocab, D, D,
                              packed + static_cast<size_t>(step) * B,

@@ -332,9 +332,15 @@ class ArcticLSTMSpeculator:
             out = torch.empty(B, S, dtype=torch.long, device=self.device)
             self._propose_into(ids, hid, out, B, S)
             return out
+        return self._replay(input_ids, previous_hidden_states, B, S).clone()   # :862-866
+
+    def _replay(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor, B: int,
+                S: int) -> torch.Tensor:
+        """Copy the inputs (device or host tensors) into the static buffers, replay the graph of the
+        padded batch and return a VIEW of the static output buffer (valid until the next call)."""
         bufs = self.static_cuda_buffers
-        bufs["last_tokens"][:B].copy_(input_ids)                       # :625
-        bufs["previous_hidden_states"][:B].copy_(previous_hidden_states)  # :629
+        bufs["last_tokens"][:B].copy_(input_ids, non_blocking=True)                        # :625
+        bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)   # :629
         padded = padding_size(B)                                       # :631
         key = (padded, S)
         g = self.cuda_graphs.get(key)
@@ -352,7 +358,7 @@ class ArcticLSTMSpeculator:
                 self._propose_into(bufs["last_tokens"], bufs["previous_hidden_states"], out_view, padded, S)
             self.cuda_graphs[key] = g
         g.replay()
-        return out_view[:B].clone()                                    # :862-866
+        return out_view[:B]
 
 
 class ArcticProposer:
@@ -363,16 +369,31 @@ class ArcticProposer:
         self.model = model
         self.device = model.device
         self.input_hidden_dim = model.input_hidden_dim
+        n = model.cuda_graph_max_batch_size
+        # pinned staging: ids go host -> static device buffer in ONE async copy, tokens come back
+        # in one; no intermediate device tensors (the reference does .to(device) / .cpu(), :160-166)
+        self._ids_pinned = torch.empty(n, dtype=torch.long).pin_memory()
+        self._out_pinned = torch.empty(n * model.max_speculative_tokens, dtype=torch.long).pin_memory()
 
     def propose(self, context_token_ids, previous_hidden_states: torch.Tensor, num_predict_tokens: int):
         assert num_predict_tokens > 0, \
             f"num_predict_tokens must be greater than 0, got {num_predict_tokens}."
-        input_ids = torch.as_tensor(context_token_ids).to(self.device, non_blocking=True)
-        if previous_hidden_states.device != self.device:
-            previous_hidden_states = previous_hidden_states.to(self.device, non_blocking=True)
-        next_tokens = self.model.generate_proposals(
-            input_ids=input_ids,
-            previous_hidden_states=previous_hidden_states,
-            num_predict_tokens=num_predict_tokens,
-        )
-        return next_tokens.cpu().numpy()
+        m = self.model
+        ids = torch.as_tensor(context_token_ids)
+        B, S = ids.shape[0], num_predict_tokens
+        fast = (m.cuda_graph_mode and 0 < B <= m.cuda_graph_max_batch_size and S <= m.max_speculative_tokens
+                and ids.dim() == 1 and previous_hidden_states.shape == (B, m.input_hidden_dim))
+        if not fast:
+            input_ids = ids.to(self.device, non_blocking=True)
+            if previous_hidden_states.device != self.device:
+                previous_hidden_states = previous_hidden_states.to(self.device, non_blocking=True)
+            return m.generate_proposals(input_ids=input_ids, previous_hidden_states=previous_hidden_states,
+                                        num_predict_tokens=S).cpu().numpy()
+        if ids.device.type == "cpu":
+            self._ids_pinned[:B].copy_(ids)
+            ids = self._ids_pinned[:B]
+        out_dev = m._replay(ids, previous_hidden_states, B, S)
+        out = self._out_pinned[:B * S].view(B, S)
+        out.copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out.numpy().copy()
