@@ -30,6 +30,22 @@ class LstmSpeculatorDesc(ctypes.Structure):
     ]
 
 
+AB200_MLP_MAX_STAGES = 8
+_PtrArr = c_void_p * AB200_MLP_MAX_STAGES
+
+
+class MlpSpeculatorDesc(ctypes.Structure):
+    """struct ab200_mlp_speculator (include/arctic_b200.h)."""
+    _fields_ = [
+        ("dtype", c_int32), ("emulate_eager_rounding", c_int32),
+        ("vocab", c_int64), ("head_rows", c_int64),
+        ("input_hidden_dim", c_int64), ("inner_dim", c_int64),
+        ("scale_input", c_int32), ("alpha", c_float), ("eps", c_float),
+        ("emb", _PtrArr), ("proj", _PtrArr), ("ln_w", _PtrArr), ("ln_b", _PtrArr), ("head", _PtrArr),
+        ("head_q", _PtrArr), ("head_scale", _PtrArr), ("fp8_head_max_batch", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/arctic_b200.h one to one
 SIGNATURES = {
     "ab200_last_error": (c_char_p, []),
@@ -74,6 +90,13 @@ SIGNATURES = {
     "ab200_lstm_propose": (c_int32, [POINTER(LstmSpeculatorDesc), c_void_p, c_void_p, c_int64,
                                      c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "ab200_sum_mlp_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int64, c_int64, c_int64, c_float, c_float, c_int32,
+                                     c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ab200_debug_mlp_generic": (c_int32, [c_int32]),
+    "ab200_mlp_workspace_bytes": (c_size_t, [POINTER(MlpSpeculatorDesc), c_int64, c_int32]),
+    "ab200_mlp_propose": (c_int32, [POINTER(MlpSpeculatorDesc), c_void_p, c_void_p, c_int64, c_int64,
+                                    c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -81,7 +81,7 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
 using namespace ab200;
 
 extern "C" const char* ab200_last_error(void) { return g_err; }
-extern "C" int32_t ab200_abi_version(void) { return 3; }
+extern "C" int32_t ab200_abi_version(void) { return 4; }
 extern "C" int64_t ab200_launch_count(void) { return g_launches; }
 extern "C" int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches) {
   g_trace_base = reinterpret_cast<unsigned long long*>(device_slots);

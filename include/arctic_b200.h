@@ -265,6 +265,55 @@ AB200_API int32_t ab200_lstm_propose(const ab200_lstm_speculator* spec,
                            void* states_out, void* cells_out,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Arctic MLP speculator / "sum_rnn" step - SURVEY 8f "next" rank 3.
+ * Replaces: ArcticMLPSpeculator.generate_states (arctic_speculator.py:265-285) and the sum_rnn
+ * branch of ArcticLSTMSpeculator.generate_states (:693-704):
+ *   state = GELU( ln( pre + alpha * emb[token] ) ),  pre = proj(x) from ab200_linear,
+ *   ln = MLPSpeculatorLayerNorm with scale and shift (:88-95).
+ * Arguments as ab200_sum_lstm_cell (pre [B, D] instead of the four gates, no cell state).
+ */
+AB200_API int32_t ab200_sum_mlp_cell(const void* pre, int64_t pre_row_stride, const void* emb_table,
+                                     const int64_t* tokens, const uint64_t* packed_argmax,
+                                     const void* ln_weight, const void* ln_bias, void* state_out,
+                                     int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
+                                     int32_t dtype, int32_t emulate_eager_rounding,
+                                     uint64_t* clear_packed, uint32_t* clear_counter,
+                                     void* state_q_out, float* state_scale_out, void* stream);
+/* test hook: 1 = generic kernel also for bf16 + emulation (must agree bit for bit) */
+AB200_API int32_t ab200_debug_mlp_generic(int32_t on);
+
+/* Whole draft loop of the MLP speculator: ln0 -> S x (proj GEMM -> fused cell -> head GEMM +
+ * arg-max).  Replaces ArcticMLPSpeculator.generate_token_ids (arctic_speculator.py:287-326) as
+ * driven by generate_proposals (:328-389), TP = 1.  Per-step weight pointers: tied checkpoints
+ * repeat the same pointer (emb/head/ln: one set; proj: first + tied), untied ones list every step. */
+#define AB200_MLP_MAX_STAGES 8
+typedef struct ab200_mlp_speculator {
+  int32_t dtype;            /* AB200_BF16 or AB200_F32 */
+  int32_t emulate_eager_rounding;
+  int64_t vocab;
+  int64_t head_rows;        /* rows of the head weights (vocab padded to 64) */
+  int64_t input_hidden_dim; /* emb_dim of the reference config: width of the base model's state */
+  int64_t inner_dim;        /* D */
+  int32_t scale_input;
+  float alpha;              /* emb_weight / state_weight (:213-215, :281) */
+  float eps;
+  const void* emb[AB200_MLP_MAX_STAGES];    /* [vocab, D] */
+  const void* proj[AB200_MLP_MAX_STAGES];   /* [D, H] for step 0, [D, D] after */
+  const void* ln_w[AB200_MLP_MAX_STAGES];   /* [D] */
+  const void* ln_b[AB200_MLP_MAX_STAGES];   /* [D] */
+  const void* head[AB200_MLP_MAX_STAGES];   /* [head_rows, D] */
+  const void* head_q[AB200_MLP_MAX_STAGES];       /* optional e4m3 copy of head (qhead) */
+  const float* head_scale[AB200_MLP_MAX_STAGES];  /* [1] each */
+  int32_t fp8_head_max_batch;
+} ab200_mlp_speculator;
+AB200_API size_t ab200_mlp_workspace_bytes(const ab200_mlp_speculator* spec, int64_t B, int32_t num_steps);
+/* states_out (optional): [num_steps, B, D] */
+AB200_API int32_t ab200_mlp_propose(const ab200_mlp_speculator* spec, const int64_t* input_ids,
+                                    const void* hidden, int64_t ld_hidden, int64_t B, int32_t num_steps,
+                                    int64_t* tokens_out, void* states_out, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ def test_ctypes_table_matches_header(built_lib):
     from arcticinference_b200 import _capi
     assert sorted(_capi.SIGNATURES) == _header_symbols()
     lib = _capi.lib()
-    assert lib.ab200_abi_version() == 3
+    assert lib.ab200_abi_version() == 4
     assert lib.ab200_last_error() == b""
 
 
