@@ -113,6 +113,206 @@ static int launch_kv(const char* keys, const char* values, int64_t krb, int64_t 
   return AB200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// FP8 KV cache (kv_cache_dtype "fp8" / "fp8_e4m3" / "fp8_e5m2") - SURVEY 8f rank 2.
+// Spec = the conversion the reference kernel was written for (dead there: ENABLE_FP8 is never
+// defined) and that vLLM's per-layer op performs: q = cvt_satfinite_fp8(float(x) / scale_layer)
+// (csrc/custom_ops/quant_utils.cuh:456-489, kernels.cu:57-66).  The correctly rounded quotient
+// is obtained without the ~10-instruction IEEE division: with r = RN(1/s), q0 = RN(x*r),
+// q = RN(q0 + fma(-q0, s, x) * r) is the correctly rounded x/s (Markstein), two at a time in
+// packed fp32.  One 16-byte source chunk -> 8 (bf16/f16) or 4 (f32) cache bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int kKvFp8MaxLayers = 64;   // 4 pointers per layer: 2 KiB of parameter space
+struct KvFp8Table {
+  char* k[kKvFp8MaxLayers];
+  char* v[kKvFp8MaxLayers];
+  const float* ks[kKvFp8MaxLayers];
+  const float* vs[kKvFp8MaxLayers];
+};
+
+// Two correctly rounded quotients {x0/s, x1/s} in packed fp32 (FMUL2 / FFMA2).  |q0| is clamped to
+// 1e6 first: beyond that the fp8 conversion saturates whatever the exact quotient, and the clamp
+// keeps inf / overflowing operands on the right side (inf stays inf, NaN re-enters through the
+// remainder) without a branch.  copysign: x = -0 has q0 = -0 but (+0 remainder)*r + (-0) = +0.
+struct kvf2 { float a, b; };
+__device__ __forceinline__ kvf2 div2_rn_by(float x0, float x1, float s, float r) {
+  kvf2 q0, rem, q;
+  asm("{ .reg .b64 x, rr, t; mov.b64 x, {%2, %3}; mov.b64 rr, {%4, %4}; mul.rn.f32x2 t, x, rr; "
+      "mov.b64 {%0, %1}, t; }"
+      : "=f"(q0.a), "=f"(q0.b)
+      : "f"(x0), "f"(x1), "f"(r));
+  const float c0 = fminf(fmaxf(q0.a, -1.0e6f), 1.0e6f), c1 = fminf(fmaxf(q0.b, -1.0e6f), 1.0e6f);
+  asm("{ .reg .b64 x, ss, c, t; mov.b64 x, {%2, %3}; mov.b64 ss, {%4, %4}; mov.b64 c, {%5, %6}; "
+      "fma.rn.f32x2 t, c, ss, x; mov.b64 {%0, %1}, t; }"
+      : "=f"(rem.a), "=f"(rem.b)
+      : "f"(x0), "f"(x1), "f"(-s), "f"(c0), "f"(c1));
+  asm("{ .reg .b64 m, rr, c, t; mov.b64 m, {%2, %3}; mov.b64 rr, {%4, %4}; mov.b64 c, {%5, %6}; "
+      "fma.rn.f32x2 t, m, rr, c; mov.b64 {%0, %1}, t; }"
+      : "=f"(q.a), "=f"(q.b)
+      : "f"(rem.a), "f"(rem.b), "f"(r), "f"(c0), "f"(c1));
+  q.a = copysignf(q.a, q0.a);
+  q.b = copysignf(q.b, q0.b);
+  return q;
+}
+
+template <bool E5M2>
+__device__ __forceinline__ uint32_t cvt2_fp8(float lo, float hi) {
+  return static_cast<uint32_t>(__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE,
+                                                        E5M2 ? __NV_E5M2 : __NV_E4M3));
+}
+
+// SRC: AB200_F32 / AB200_F16 / AB200_BF16.  Returns the packed fp8 bytes of one 16-byte chunk
+// (8 bytes in .x/.y for 2-byte sources, 4 bytes in .x for f32).
+template <int SRC, bool E5M2>
+__device__ __forceinline__ uint2 quant_chunk(const uint4& in, float s, float r) {
+  uint2 out = make_uint2(0u, 0u);
+  if constexpr (SRC == AB200_F32) {
+    const kvf2 a = div2_rn_by(__uint_as_float(in.x), __uint_as_float(in.y), s, r);
+    const kvf2 b = div2_rn_by(__uint_as_float(in.z), __uint_as_float(in.w), s, r);
+    out.x = cvt2_fp8<E5M2>(a.a, a.b) | (cvt2_fp8<E5M2>(b.a, b.b) << 16);
+  } else {
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    uint32_t q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      if constexpr (SRC == AB200_BF16) {
+        lo = __uint_as_float(w[j] << 16);
+        hi = __uint_as_float(w[j] & 0xffff0000u);
+      } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+        lo = __low2float(h);
+        hi = __high2float(h);
+      }
+      const kvf2 d = div2_rn_by(lo, hi, s, r);
+      q[j] = cvt2_fp8<E5M2>(d.a, d.b);
+    }
+    out.x = q[0] | (q[1] << 16);
+    out.y = q[2] | (q[3] << 16);
+  }
+  return out;
+}
+
+template <int SRC, bool E5M2>
+__global__ void __launch_bounds__(kKvThreads)
+kv_write_bulk_fp8_kernel(const char* __restrict__ keys, const char* __restrict__ values,
+                         int64_t key_row_bytes, int64_t value_row_bytes,
+                         const __grid_constant__ KvFp8Table tbl,
+                         const int64_t* __restrict__ slot_mapping, int64_t block_stride_bytes,
+                         int32_t block_size, uint32_t row_elems, uint32_t chunks_per_row,
+                         int32_t cpr_shift, uint32_t total_chunks) {
+  constexpr int EPC = SRC == AB200_F32 ? 4 : 8;   // elements (= cache bytes) per 16-byte chunk
+  const int64_t token = blockIdx.x;
+  const int64_t slot = __ldg(slot_mapping + token);
+  if (slot < 0) return;
+  const int64_t blk = slot / block_size;
+  const int64_t off = slot - blk * block_size;
+  const int64_t dst_row = blk * block_stride_bytes + off * static_cast<int64_t>(row_elems);
+  const char* ksrc = keys + token * key_row_bytes;
+  const char* vsrc = values + token * value_row_bytes;
+  const uint32_t q0 = blockIdx.y * (kKvThreads * kKvUnroll) + threadIdx.x;
+  uint4 kreg[kKvUnroll], vreg[kKvUnroll];
+#pragma unroll
+  for (int j = 0; j < kKvUnroll; ++j) {
+    const uint32_t q = q0 + j * kKvThreads;
+    if (q < total_chunks) {
+      kreg[j] = ld_stream_16(ksrc + static_cast<int64_t>(q) * 16);
+      vreg[j] = ld_stream_16(vsrc + static_cast<int64_t>(q) * 16);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kKvUnroll; ++j) {
+    const uint32_t q = q0 + j * kKvThreads;
+    if (q < total_chunks) {
+      const uint32_t layer = cpr_shift >= 0 ? (q >> cpr_shift) : (q / chunks_per_row);
+      const uint32_t c = q - layer * chunks_per_row;
+      const int64_t d = dst_row + static_cast<int64_t>(c) * EPC;
+      const float sk = __ldg(tbl.ks[layer]), sv = __ldg(tbl.vs[layer]);
+      const uint2 qk = quant_chunk<SRC, E5M2>(kreg[j], sk, __frcp_rn(sk));
+      const uint2 qv = quant_chunk<SRC, E5M2>(vreg[j], sv, __frcp_rn(sv));
+      if constexpr (EPC == 8) {
+        *reinterpret_cast<uint2*>(tbl.k[layer] + d) = qk;
+        *reinterpret_cast<uint2*>(tbl.v[layer] + d) = qv;
+      } else {
+        *reinterpret_cast<uint32_t*>(tbl.k[layer] + d) = qk.x;
+        *reinterpret_cast<uint32_t*>(tbl.v[layer] + d) = qv.x;
+      }
+    }
+  }
+}
+
+template <int SRC, bool E5M2>
+static int launch_kv_fp8(const char* keys, const char* values, int64_t krb, int64_t vrb,
+                         const KvFp8Table& tbl, int layers, const int64_t* slot_mapping,
+                         int64_t num_tokens, int64_t bsb, int32_t block_size, uint32_t row_elems,
+                         cudaStream_t stream) {
+  constexpr int EPC = SRC == AB200_F32 ? 4 : 8;
+  const uint32_t cpr = row_elems / EPC;
+  int shift = -1;
+  if ((cpr & (cpr - 1)) == 0) {
+    shift = 0;
+    while ((1u << shift) < cpr) ++shift;
+  }
+  const uint32_t total = cpr * static_cast<uint32_t>(layers);
+  const uint32_t per_cta = kKvThreads * kKvUnroll;
+  dim3 grid(static_cast<unsigned>(num_tokens), (total + per_cta - 1) / per_cta);
+  kv_write_bulk_fp8_kernel<SRC, E5M2><<<grid, kKvThreads, 0, stream>>>(
+      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_elems, cpr, shift, total);
+  AB200_CHECK_LAUNCH("kv_write_bulk_fp8_kernel");
+  return AB200_OK;
+}
+
+static int kv_write_fp8(const void* keys, const void* values, int64_t key_row_stride,
+                        int64_t value_row_stride, void* const* key_cache_ptrs,
+                        void* const* value_cache_ptrs, const float* const* k_scale_ptrs,
+                        const float* const* v_scale_ptrs, int32_t num_layers,
+                        const int64_t* slot_mapping, int64_t num_tokens, int64_t block_stride,
+                        int32_t block_size, int64_t n, int32_t src_dtype, bool e5m2, cudaStream_t s) {
+  AB200_REQUIRE(k_scale_ptrs && v_scale_ptrs, AB200_E_INVALID,
+                "kv_write_bulk: fp8 kv cache needs k_scales / v_scales");
+  const int e = dtype_bytes(src_dtype);
+  const int epc = 16 / e;
+  AB200_REQUIRE(n % epc == 0 && key_row_stride % epc == 0 && value_row_stride % epc == 0 &&
+                    block_stride % epc == 0 && aligned(keys, 16) && aligned(values, 16),
+                AB200_E_INVALID,
+                "kv_write_bulk: fp8 kv cache needs num_heads*head_size, the row strides and the block "
+                "stride to be multiples of %d and 16-byte aligned sources", epc);
+  const int64_t krb = key_row_stride * e, vrb = value_row_stride * e;
+  for (int l0 = 0; l0 < num_layers; l0 += kKvFp8MaxLayers) {
+    const int layers = num_layers - l0 < kKvFp8MaxLayers ? num_layers - l0 : kKvFp8MaxLayers;
+    KvFp8Table tbl;
+    for (int l = 0; l < kKvFp8MaxLayers; ++l) {
+      const bool in = l < layers;
+      tbl.k[l] = in ? static_cast<char*>(key_cache_ptrs[l0 + l]) : nullptr;
+      tbl.v[l] = in ? static_cast<char*>(value_cache_ptrs[l0 + l]) : nullptr;
+      tbl.ks[l] = in ? k_scale_ptrs[l0 + l] : nullptr;
+      tbl.vs[l] = in ? v_scale_ptrs[l0 + l] : nullptr;
+      if (in)
+        AB200_REQUIRE(tbl.k[l] && tbl.v[l] && tbl.ks[l] && tbl.vs[l] && aligned(tbl.k[l], epc) &&
+                          aligned(tbl.v[l], epc),
+                      AB200_E_INVALID, "kv_write_bulk: NULL or misaligned cache / scale pointer for layer %d",
+                      l0 + l);
+    }
+    const char* kp = static_cast<const char*>(keys) + static_cast<int64_t>(l0) * n * e;
+    const char* vp = static_cast<const char*>(values) + static_cast<int64_t>(l0) * n * e;
+    int rc;
+#define AB200_KV8(SRC)                                                                           \
+  (e5m2 ? launch_kv_fp8<SRC, true>(kp, vp, krb, vrb, tbl, layers, slot_mapping, num_tokens,      \
+                                   block_stride, block_size, static_cast<uint32_t>(n), s)        \
+        : launch_kv_fp8<SRC, false>(kp, vp, krb, vrb, tbl, layers, slot_mapping, num_tokens,     \
+                                    block_stride, block_size, static_cast<uint32_t>(n), s))
+    switch (src_dtype) {
+      case AB200_F32: rc = AB200_KV8(AB200_F32); break;
+      case AB200_F16: rc = AB200_KV8(AB200_F16); break;
+      default: rc = AB200_KV8(AB200_BF16); break;
+    }
+#undef AB200_KV8
+    if (rc != AB200_OK) return rc;
+  }
+  return AB200_OK;
+}
+
 }  // namespace ab200
 
 using namespace ab200;
@@ -126,16 +326,13 @@ extern "C" int32_t ab200_kv_write_bulk(const void* keys, const void* values,
                                        int64_t block_stride, int32_t block_size,
                                        int32_t num_heads, int32_t head_size, int32_t src_dtype,
                                        int32_t kv_dtype, void* stream) {
-  (void)k_scale_ptrs;
-  (void)v_scale_ptrs;
   if (num_layers == 0 || num_tokens == 0) return AB200_OK;  // kernels.cu:99-101
   AB200_REQUIRE(num_layers > 0 && num_tokens > 0, AB200_E_INVALID,
                 "kv_write_bulk: negative num_layers/num_tokens");
   AB200_REQUIRE(src_dtype == AB200_F32 || src_dtype == AB200_F16 || src_dtype == AB200_BF16,
                 AB200_E_INVALID, "kv_write_bulk: unsupported src dtype %d", src_dtype);
-  AB200_REQUIRE(kv_dtype == AB200_KV_AUTO, AB200_E_UNSUPPORTED,
-                "kv_write_bulk: fp8 kv_cache_dtype is not built (dead code in the reference: "
-                "ENABLE_FP8 undefined)");
+  AB200_REQUIRE(kv_dtype == AB200_KV_AUTO || kv_dtype == AB200_KV_FP8_E4M3 || kv_dtype == AB200_KV_FP8_E5M2,
+                AB200_E_UNSUPPORTED, "kv_write_bulk: unsupported kv cache dtype %d", kv_dtype);
   AB200_REQUIRE(keys && values && key_cache_ptrs && value_cache_ptrs && slot_mapping,
                 AB200_E_INVALID, "kv_write_bulk: NULL pointer argument");
   AB200_REQUIRE(block_size > 0 && num_heads > 0 && head_size > 0, AB200_E_INVALID,
@@ -149,6 +346,11 @@ extern "C" int32_t ab200_kv_write_bulk(const void* keys, const void* values,
                 "kv_write_bulk: num_heads*head_size too large");
   AB200_REQUIRE(key_row_stride >= n * num_layers && value_row_stride >= n * num_layers,
                 AB200_E_INVALID, "kv_write_bulk: source row stride smaller than num_layers*n");
+  if (kv_dtype != AB200_KV_AUTO)   // block_stride counts cache elements = bytes
+    return kv_write_fp8(keys, values, key_row_stride, value_row_stride, key_cache_ptrs, value_cache_ptrs,
+                        k_scale_ptrs, v_scale_ptrs, num_layers, slot_mapping, num_tokens, block_stride,
+                        block_size, n, src_dtype, kv_dtype == AB200_KV_FP8_E5M2,
+                        static_cast<cudaStream_t>(stream));
   const int64_t krb = key_row_stride * e, vrb = value_row_stride * e, bsb = block_stride * e;
 
   // widest vector every address involved is aligned to

@@ -71,6 +71,9 @@ def _reshape_and_cache_flash_bulk_cuda(keys: torch.Tensor, values: torch.Tensor,
     if kv_cache_dtype == "auto":
         _check(keys.dtype == values.dtype == key_caches[0].dtype == value_caches[0].dtype,
                "keys/values/cache dtypes must match for kv_cache_dtype='auto'")
+    else:
+        _check(key_caches[0].element_size() == 1 and value_caches[0].element_size() == 1,
+               "fp8 kv cache needs a one-byte cache dtype (uint8 / float8)")
     _check(slot_mapping.dtype == torch.int64, "expected scalar type Long for slot_mapping")
     num_tokens = slot_mapping.size(0)                                 # kernels.cu:108
     if num_tokens == 0:

@@ -65,12 +65,17 @@ AB200_API int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_lau
  *   value_cache_l[slot / block_size][slot % block_size][0 .. n) = values[t][l*n .. (l+1)*n)
  * with n = num_heads * head_size; a cache block is `block_stride` elements apart (bs*n for vLLM's
  * FlashAttention layout, 2*bs*n for FlashInfer's), dense [block_size, n] inside.  Bit-exact copy
- * for kv_dtype AB200_KV_AUTO.  FP8 KV (dead code in the reference: ENABLE_FP8 is never defined,
- * csrc/custom_ops/quant_utils.cuh:13,515-526) returns AB200_E_UNSUPPORTED.
+ * for kv_dtype AB200_KV_AUTO.  AB200_KV_FP8_E4M3 / _E5M2 (one-byte cache
+ * elements): q = cvt_satfinite_fp8(float(x) / *k_scale_ptrs[l]) - the conversion the reference
+ * kernel was written for (csrc/custom_ops/quant_utils.cuh:456-489, kernels.cu:57-66; dead code
+ * there because ENABLE_FP8 is never defined) and that vLLM's per-layer op performs; pinned against
+ * vLLM's op on a B200 (tests/test_kv_write_fp8_gpu.py).  Needs n and the strides to be multiples
+ * of 16 / sizeof(src element).
  *
  * key_cache_ptrs / value_cache_ptrs: HOST arrays of num_layers device pointers.  They are passed
  * to the kernel by value (no per-call H2D copy, unlike kernels.cu:135-146).
- * k_scale_ptrs / v_scale_ptrs: HOST arrays of device float* (ignored for AUTO; may be NULL).
+ * k_scale_ptrs / v_scale_ptrs: HOST arrays of device float* (one scalar per layer, read on the
+ * device; ignored for AUTO, where they may be NULL).
  * num_layers == 0 or num_tokens == 0 is a successful no-op (kernels.cu:99-101).
  */
 AB200_API int32_t ab200_kv_write_bulk(const void* keys, const void* values,

@@ -124,7 +124,7 @@ def test_error_behaviour(ops):
         ops.reshape_and_cache_flash_bulk(k, k, [c, c], [c], sm, "auto", s, s, 2, 8)
     with pytest.raises(RuntimeError):   # unknown kv cache dtype (quant_utils.cuh:567)
         ops.reshape_and_cache_flash_bulk(k, k, [c, c], [c, c], sm, "int4", s, s, 2, 8)
-    with pytest.raises(RuntimeError, match="fp8"):   # dead in the reference; unsupported here
+    with pytest.raises(RuntimeError, match="fp8"):   # fp8 needs a one-byte cache dtype
         ops.reshape_and_cache_flash_bulk(k, k, [c, c], [c, c], sm, "fp8", s, s, 2, 8)
     with pytest.raises(RuntimeError):   # int32 slot mapping (data_ptr<int64_t>() throws)
         ops.reshape_and_cache_flash_bulk(k, k, [c, c], [c, c], sm.int(), "auto", s, s, 2, 8)

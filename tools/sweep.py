@@ -174,6 +174,16 @@ def sweep_kv(rows):
                      "gbs": alg / t / 1e3, "hbm_frac": alg / t / 1e3 / HBM, "frac_of_8TBs": alg / t / 1e3 / 8000})
         print(f"[kv {name}] {t:8.1f} us {alg / t / 1e3:6.0f} GB/s ({alg / t / 1e3 / HBM:.2f} of measured peak, "
               f"{alg / t / 1e3 / 8000:.2f} of 8 TB/s)  [includes ~host launch path of the torch op]", flush=True)
+        if layout == "flash" and T >= 8192:
+            kv8 = [torch.zeros(2, nb, bs, Hkv, Dh, device=dev, dtype=torch.uint8) for _ in range(L)]
+            kc8, vc8 = [x[0] for x in kv8], [x[1] for x in kv8]
+            sc8 = [torch.full((), 0.05 * (i + 1), device=dev) for i in range(L)]
+            t8 = timeit(lambda: py_custom_ops.reshape_and_cache_flash_bulk(keys, vals, kc8, vc8, slots, "fp8", sc8, sc8, Hkv, Dh))
+            alg8 = valid * L * n * 2 * 3 + 8 * T
+            rows.append({"kernel": "kv_write_bulk_fp8", "case": name, "L": L, "T": T, "n": n, "us": t8,
+                         "gbs": alg8 / t8 / 1e3, "hbm_frac": alg8 / t8 / 1e3 / HBM})
+            print(f"[kv fp8 {name}] {t8:8.1f} us {alg8 / t8 / 1e3:6.0f} GB/s ({alg8 / t8 / 1e3 / HBM:.2f} of measured peak)", flush=True)
+            del kv8, kc8, vc8
         del kv, kc, vc, keys, vals
 
 
