@@ -389,3 +389,90 @@ extern "C" int32_t ab200_kv_write_bulk(const void* keys, const void* values,
   }
   return AB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// SwiftKV select: gather the surviving ("logit") tokens' rows of several tensors in one launch.
+// Replaces the five torch.index_select calls of LlamaSwiftKVModel.swiftkv_select
+// (arctic_inference/vllm/swiftkv/llama_swiftkv.py:669-685: hidden_states, residual, positions,
+// k_states, v_states by final_logits_indices).  Byte copy, HBM/latency-bound, graph-capturable.
+// ------------------------------------------------------------------------------------------
+namespace ab200 {
+constexpr int kGatherMaxTensors = 8;
+struct GatherTable {
+  const char* src[kGatherMaxTensors];
+  char* dst[kGatherMaxTensors];
+  int64_t src_stride[kGatherMaxTensors];   // bytes between rows
+  int64_t dst_stride[kGatherMaxTensors];
+  uint32_t row_bytes[kGatherMaxTensors];
+  uint32_t chunk_begin[kGatherMaxTensors + 1];   // prefix sums of 16-byte chunks (rounded up) per row
+  int32_t vec16[kGatherMaxTensors];        // 1: 16-byte vector path is legal for this tensor
+  int32_t count;
+};
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restrict__ indices,
+                   int64_t num_src_rows) {
+  const int64_t out_row = blockIdx.x;
+  int64_t src_row = __ldg(indices + out_row);
+  if (src_row < 0) src_row += num_src_rows;                       // torch index_select accepts negatives
+  if (src_row < 0 || src_row >= num_src_rows) return;             // (host validates; never read outside)
+  const uint32_t total = t.chunk_begin[t.count];
+  for (uint32_t q = blockIdx.y * blockDim.x + threadIdx.x; q < total; q += gridDim.y * blockDim.x) {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kGatherMaxTensors; ++i)
+      if (i < t.count && q >= t.chunk_begin[i]) k = i;
+    const uint32_t c = q - t.chunk_begin[k];
+    const char* s = t.src[k] + src_row * t.src_stride[k] + static_cast<int64_t>(c) * 16;
+    char* d = t.dst[k] + out_row * t.dst_stride[k] + static_cast<int64_t>(c) * 16;
+    const uint32_t left = t.row_bytes[k] - c * 16;
+    if (t.vec16[k] && left >= 16) {
+      st_stream_16(d, ld_stream_16(s));
+    } else {
+      const uint32_t nb = left < 16 ? left : 16;
+      for (uint32_t b = 0; b < nb; ++b) d[b] = s[b];
+    }
+  }
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_gather_rows(const void* const* src_ptrs, void* const* dst_ptrs,
+                                     const int64_t* src_row_strides_bytes,
+                                     const int64_t* dst_row_strides_bytes, const int64_t* row_bytes,
+                                     int32_t num_tensors, const int64_t* indices, int64_t num_indices,
+                                     int64_t num_src_rows, void* stream) {
+  if (num_tensors == 0 || num_indices == 0) return AB200_OK;
+  AB200_REQUIRE(num_tensors > 0 && num_tensors <= kGatherMaxTensors, AB200_E_INVALID,
+                "gather_rows: 1..%d tensors per call", kGatherMaxTensors);
+  AB200_REQUIRE(src_ptrs && dst_ptrs && src_row_strides_bytes && dst_row_strides_bytes && row_bytes &&
+                    indices && num_indices > 0 && num_src_rows > 0 && num_indices <= 0x7fffffffLL,
+                AB200_E_INVALID, "gather_rows: bad arguments");
+  GatherTable t;
+  uint32_t acc = 0;
+  for (int i = 0; i < kGatherMaxTensors; ++i) {
+    const bool in = i < num_tensors;
+    t.src[i] = in ? static_cast<const char*>(src_ptrs[i]) : nullptr;
+    t.dst[i] = in ? static_cast<char*>(dst_ptrs[i]) : nullptr;
+    t.src_stride[i] = in ? src_row_strides_bytes[i] : 0;
+    t.dst_stride[i] = in ? dst_row_strides_bytes[i] : 0;
+    t.row_bytes[i] = in ? static_cast<uint32_t>(row_bytes[i]) : 0;
+    t.chunk_begin[i] = acc;
+    t.vec16[i] = 0;
+    if (in) {
+      AB200_REQUIRE(t.src[i] && t.dst[i] && row_bytes[i] > 0 && row_bytes[i] < (1LL << 31), AB200_E_INVALID,
+                    "gather_rows: NULL pointer or bad row size for tensor %d", i);
+      t.vec16[i] = aligned(t.src[i], 16) && aligned(t.dst[i], 16) && t.src_stride[i] % 16 == 0 &&
+                   t.dst_stride[i] % 16 == 0;
+      acc += (t.row_bytes[i] + 15) / 16;
+    }
+  }
+  t.chunk_begin[kGatherMaxTensors] = acc;
+  for (int i = num_tensors; i <= kGatherMaxTensors; ++i) t.chunk_begin[i] = acc;
+  t.count = num_tensors;
+  unsigned gy = (acc + 255) / 256;
+  if (gy > 64) gy = 64;
+  dim3 grid(static_cast<unsigned>(num_indices), gy);
+  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, indices, num_src_rows);
+  AB200_CHECK_LAUNCH("gather_rows_kernel");
+  return AB200_OK;
+}

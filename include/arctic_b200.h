@@ -88,6 +88,18 @@ AB200_API int32_t ab200_kv_write_bulk(const void* keys, const void* values,
                             int32_t num_heads, int32_t head_size,
                             int32_t src_dtype, int32_t kv_dtype, void* stream);
 
+/* SwiftKV select: dst_i[j, :] = src_i[indices[j], :] for up to 8 tensors in
+ * ONE launch.  Replaces the five torch.index_select calls of LlamaSwiftKVModel.swiftkv_select
+ * (arctic_inference/vllm/swiftkv/llama_swiftkv.py:669-685) that compact hidden_states, residual,
+ * positions, k_states and v_states to the surviving tokens.  Host arrays of num_tensors entries;
+ * strides and row sizes in bytes; indices [num_indices] int64 on the device, each in
+ * [-num_src_rows, num_src_rows) (out-of-range rows are skipped, never read). */
+AB200_API int32_t ab200_gather_rows(const void* const* src_ptrs, void* const* dst_ptrs,
+                                    const int64_t* src_row_strides_bytes,
+                                    const int64_t* dst_row_strides_bytes, const int64_t* row_bytes,
+                                    int32_t num_tensors, const int64_t* indices, int64_t num_indices,
+                                    int64_t num_src_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Hot path A: Arctic LSTM speculator draft head (method "sum_lstm").
  * Replaces the eager-PyTorch op sequences inside

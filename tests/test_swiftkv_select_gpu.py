@@ -1,0 +1,83 @@
+"""GPU: SwiftKV select (llama_swiftkv.py:599-685) - the fused row gather is bit-exact against
+torch.index_select, the whole step (bulk KV write + compaction) against the reference's op
+sequence restated with torch ops."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("T,hid,Ln,B", [(300, 4096, 16 * 1024, 17), (64, 2880, 18 * 512, 64), (9, 40, 12, 5),
+                                       (1000, 8192, 1024, 256)])
+def test_gather_rows_matches_index_select(T, hid, Ln, B):
+    from arcticinference_b200.swiftkv import gather_rows
+    g = torch.Generator(device="cpu").manual_seed(T + B)
+    hs = torch.randn(T, hid, generator=g).to(torch.bfloat16).to(DEV)
+    res = torch.randn(T, hid, generator=g).to(torch.bfloat16).to(DEV)
+    pos = torch.randint(0, 100000, (T,), generator=g).to(DEV)
+    ks = torch.randn(T, Ln + 8, generator=g).to(torch.bfloat16).to(DEV)[:, :Ln]      # strided source rows
+    vs = torch.randn(T, Ln, generator=g).to(torch.float16).to(DEV)
+    idx = torch.randint(0, T, (B,), generator=g).to(DEV)
+    idx[0] = -1                                                                     # negative index
+    got = gather_rows([hs, res, pos, ks, vs], idx)
+    for a, t in zip(got, [hs, res, pos, ks, vs]):
+        assert torch.equal(a, t.index_select(0, idx % T))
+
+
+def test_gather_rows_into_buffers_and_edge_cases():
+    from arcticinference_b200.swiftkv import gather_rows
+    x = torch.arange(50 * 7, device=DEV, dtype=torch.float32).reshape(50, 7)       # 28-byte rows: byte path
+    y = torch.arange(50, device=DEV, dtype=torch.int64)
+    buf = torch.full((16, 7), -1.0, device=DEV)
+    idx = torch.tensor([3, 49, 0], device=DEV)
+    a, b = gather_rows([x, y], idx, [buf, None])
+    assert a.data_ptr() == buf.data_ptr() and torch.equal(buf[:3], x[idx]) and (buf[3:] == -1).all()
+    assert torch.equal(b, y[idx])
+    assert gather_rows([x], idx[:0])[0].shape == (0, 7)
+    with pytest.raises(RuntimeError):
+        gather_rows([x], idx.int())
+    with pytest.raises(NotImplementedError):
+        gather_rows([x.cpu()], idx.cpu())
+
+
+def test_swiftkv_select_step_matches_reference_sequence():
+    from arcticinference_b200.swiftkv import swiftkv_select
+    L, T, Hkv, Dh, bs, hid, B = 4, 200, 8, 64, 16, 1024, 6
+    n = Hkv * Dh
+    nb = 2 * ((T + bs - 1) // bs)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    hs = torch.randn(T, hid, generator=g).to(torch.bfloat16).to(DEV)
+    res = torch.randn(T, hid, generator=g).to(torch.bfloat16).to(DEV)
+    pos = torch.arange(T).to(DEV)
+    k = torch.randn(T, L * n, generator=g).to(torch.bfloat16).to(DEV)
+    v = torch.randn(T, L * n, generator=g).to(torch.bfloat16).to(DEV)
+    slots = torch.randperm(nb * bs, generator=g)[:T].to(DEV)
+    logits_idx = torch.tensor([10, 50, 51, 120, 199, 0], device=DEV)
+    caches = [torch.zeros(2, nb, bs, Hkv, Dh, dtype=torch.bfloat16, device=DEV) for _ in range(L)]
+    ref_caches = [c.clone() for c in caches]
+    sc = [torch.ones((), device=DEV) for _ in range(L)]
+    bufs = {"hidden_states": torch.zeros(8, hid, dtype=torch.bfloat16, device=DEV),
+            "residual": torch.zeros(8, hid, dtype=torch.bfloat16, device=DEV),
+            "positions": torch.zeros(8, dtype=torch.long, device=DEV),
+            "k_states": torch.zeros(8, L * n, dtype=torch.bfloat16, device=DEV),
+            "v_states": torch.zeros(8, L * n, dtype=torch.bfloat16, device=DEV)}
+    out = swiftkv_select(hs, res, pos, k, v, key_caches=[c[0] for c in caches], value_caches=[c[1] for c in caches],
+                         slot_mapping=slots, kv_cache_dtype="auto", k_scales=sc, v_scales=sc, num_kv_heads=Hkv,
+                         head_size=Dh, logits_indices=logits_idx, graph_buffers=bufs, cuda_graph_max_batch_size=8,
+                         pad_for_cudagraph=lambda b: 8)
+    # the reference's sequence: per-layer scatter (:630-656 semantics) + five index_selects (:669-685)
+    blk, off = slots // bs, slots % bs
+    for l in range(L):
+        ref_caches[l][0][blk, off] = k[:, l * n:(l + 1) * n].reshape(T, Hkv, Dh)
+        ref_caches[l][1][blk, off] = v[:, l * n:(l + 1) * n].reshape(T, Hkv, Dh)
+        assert torch.equal(caches[l], ref_caches[l])
+    for o, t in zip(out, (hs, res, pos, k, v)):
+        assert o.shape[0] == 8
+        assert torch.equal(o[:B], t.index_select(0, logits_idx))
+    # above the graph batch limit: fresh tensors, no padding
+    out2 = swiftkv_select(hs, res, pos, k, v, key_caches=[], value_caches=[], slot_mapping=slots,
+                          kv_cache_dtype="auto", k_scales=[], v_scales=[], num_kv_heads=Hkv, head_size=Dh,
+                          logits_indices=logits_idx, graph_buffers=bufs, cuda_graph_max_batch_size=4)
+    assert out2[0].shape[0] == B and torch.equal(out2[3], k.index_select(0, logits_idx))
