@@ -90,6 +90,8 @@ SIGNATURES = {
     "ab200_lstm_propose": (c_int32, [POINTER(LstmSpeculatorDesc), c_void_p, c_void_p, c_int64,
                                      c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "ab200_select_hidden_rows": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32, c_void_p,
+                                           c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "ab200_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                     c_int64, c_int64, c_void_p]),
     "ab200_sum_mlp_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -47,6 +47,33 @@ __global__ void unpack_steps_kernel(const unsigned long long* __restrict__ packe
   }
 }
 
+// ArcticProposer.prepare_hidden_states (arctic_proposer.py:113-147): request r keeps the hidden
+// state of its LAST accepted token: row (gen_len[r] - 1) + row_offsets[r] of sample_hidden_states,
+// gen_len[r] = #(sampled_token_ids[r, :] != -1), row_offsets = exclusive cumsum of (num_draft + 1).
+// One CTA per request; replaces ne / sum / cumsum / sub / add / index (8 ATen launches).
+__global__ void __launch_bounds__(256)
+select_hidden_rows_kernel(const char* __restrict__ hidden, int64_t row_stride_bytes, int64_t num_rows,
+                          const int64_t* __restrict__ sampled, int64_t ld_sampled, int32_t max_gen_len,
+                          const int64_t* __restrict__ row_offsets, char* __restrict__ out,
+                          int64_t out_stride_bytes, uint32_t row_bytes, int32_t vec16) {
+  const int64_t r = blockIdx.x;
+  int gen = 0;
+  for (int g = 0; g < max_gen_len; ++g) gen += __ldg(sampled + r * ld_sampled + g) != -1;
+  int64_t src = (gen - 1) + __ldg(row_offsets + r);
+  // gen == 0 indexes row offset-1 in the reference (negative wraps in torch); clamp into the tensor
+  if (src < 0) src += num_rows;
+  if (src < 0 || src >= num_rows) return;
+  const char* s = hidden + src * row_stride_bytes;
+  char* d = out + r * out_stride_bytes;
+  if (vec16) {
+    for (uint32_t q = threadIdx.x; q < row_bytes / 16; q += blockDim.x)
+      st_stream_16(d + q * 16ull, ld_stream_16(s + q * 16ull));
+    for (uint32_t b = (row_bytes / 16) * 16 + threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = s[b];
+  } else {
+    for (uint32_t b = threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = s[b];
+  }
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
@@ -185,5 +212,24 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
         reinterpret_cast<const unsigned long long*>(packed), tokens_out, B, num_steps);
     AB200_CHECK_LAUNCH("unpack_steps_kernel");
   }
+  return AB200_OK;
+}
+
+extern "C" int32_t ab200_select_hidden_rows(const void* sample_hidden, int64_t hidden_row_stride_bytes,
+                                            int64_t num_hidden_rows, const int64_t* sampled_token_ids,
+                                            int64_t sampled_row_stride, int32_t max_gen_len,
+                                            const int64_t* row_offsets, int64_t num_requests, void* out,
+                                            int64_t out_row_stride_bytes, int64_t row_bytes, void* stream) {
+  if (num_requests == 0) return AB200_OK;
+  AB200_REQUIRE(sample_hidden && sampled_token_ids && row_offsets && out && num_requests > 0 &&
+                    num_hidden_rows > 0 && max_gen_len > 0 && row_bytes > 0 && row_bytes < (1LL << 31),
+                AB200_E_INVALID, "select_hidden_rows: bad arguments");
+  const int vec = aligned(sample_hidden, 16) && aligned(out, 16) && hidden_row_stride_bytes % 16 == 0 &&
+                  out_row_stride_bytes % 16 == 0;
+  select_hidden_rows_kernel<<<static_cast<unsigned>(num_requests), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const char*>(sample_hidden), hidden_row_stride_bytes, num_hidden_rows, sampled_token_ids,
+      sampled_row_stride, max_gen_len, row_offsets, static_cast<char*>(out), out_row_stride_bytes,
+      static_cast<uint32_t>(row_bytes), vec);
+  AB200_CHECK_LAUNCH("select_hidden_rows_kernel");
   return AB200_OK;
 }

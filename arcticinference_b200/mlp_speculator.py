@@ -172,7 +172,9 @@ class ArcticMLPSpeculator:
         need = self._lib.ab200_mlp_workspace_bytes(ctypes.byref(self._descriptor()), batch, steps)
         if self._workspace is None or self._workspace.numel() < need:
             if self.cuda_graphs:
-                raise RuntimeError("workspace would have to grow after CUDA graphs were captured")
+                # a batch above the graph limit (eager path): the captured graphs keep pointing at
+                # the original workspace, this call gets its own
+                return torch.empty(need, dtype=torch.uint8, device=self.device)
             biggest = self._lib.ab200_mlp_workspace_bytes(
                 ctypes.byref(self._descriptor()), max(batch, self.cuda_graph_max_batch_size),
                 max(steps, self.max_speculative_tokens))

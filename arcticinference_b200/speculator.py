@@ -206,7 +206,9 @@ class ArcticLSTMSpeculator:
         need = self._lib.ab200_lstm_workspace_bytes(ctypes.byref(self._descriptor()), batch, steps)
         if self._workspace is None or self._workspace.numel() < need:
             if self.cuda_graphs:
-                raise RuntimeError("workspace would have to grow after CUDA graphs were captured")
+                # a batch above the graph limit (eager path): the captured graphs keep pointing at
+                # the original workspace, this call gets its own
+                return torch.empty(need, dtype=torch.uint8, device=self.device)
             biggest = self._lib.ab200_lstm_workspace_bytes(
                 ctypes.byref(self._descriptor()),
                 max(batch, self.cuda_graph_max_batch_size), max(steps, self.max_speculative_tokens))
@@ -374,6 +376,36 @@ class ArcticProposer:
         # in one; no intermediate device tensors (the reference does .to(device) / .cpu(), :160-166)
         self._ids_pinned = torch.empty(n, dtype=torch.long).pin_memory()
         self._out_pinned = torch.empty(n * model.max_speculative_tokens, dtype=torch.long).pin_memory()
+
+    def prepare_hidden_states(self, sample_hidden_states: torch.Tensor, sampled_token_ids: torch.Tensor,
+                              num_draft_tokens: Optional[List[int]]) -> torch.Tensor:
+        """arctic_proposer.py:113-147: keep, for every request, the hidden state of its last accepted
+        token.  ``sampled_token_ids`` [R, max_gen_len] int64 (-1 = rejected / padding),
+        ``num_draft_tokens`` = spec_decode_metadata.num_draft_tokens (host list).  One launch."""
+        if sample_hidden_states is not None:
+            assert sample_hidden_states.shape[-1] == self.input_hidden_dim, \
+                (f"hidden_states shape mismatch: {sample_hidden_states.shape[-1]} != {self.input_hidden_dim}. "
+                 "Please make sure spec model is trained using the same base model.")
+        max_gen_len = sampled_token_ids.shape[-1]
+        if max_gen_len == 1:                                              # :134-136
+            return sample_hidden_states
+        assert num_draft_tokens is not None
+        R = sampled_token_ids.shape[0]
+        h = sample_hidden_states
+        if h.stride(-1) != 1:
+            h = h.contiguous()
+        ids = sampled_token_ids.to(device=self.device, dtype=torch.long)
+        if ids.stride(-1) != 1:
+            ids = ids.contiguous()
+        counts = torch.as_tensor(num_draft_tokens, dtype=torch.long) + 1
+        offs = (torch.cumsum(counts, 0) - counts).to(self.device, non_blocking=True)   # exclusive cumsum
+        out = torch.empty(R, h.shape[1], dtype=h.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib().ab200_select_hidden_rows(
+                h.data_ptr(), h.stride(0) * h.element_size(), h.shape[0], ids.data_ptr(), ids.stride(0),
+                max_gen_len, offs.data_ptr(), R, out.data_ptr(), out.stride(0) * out.element_size(),
+                h.shape[1] * h.element_size(), _capi.current_stream_ptr(self.device)), "ab200_select_hidden_rows")
+        return out
 
     def propose(self, context_token_ids, previous_hidden_states: torch.Tensor, num_predict_tokens: int):
         assert num_predict_tokens > 0, \

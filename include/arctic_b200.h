@@ -282,6 +282,18 @@ AB200_API int32_t ab200_lstm_propose(const ab200_lstm_speculator* spec,
                            void* states_out, void* cells_out,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Drafter glue: ArcticProposer.prepare_hidden_states
+ * (arctic_inference/vllm/spec_dec/arctic_proposer.py:113-147).  For request r:
+ *   gen_len = #(sampled_token_ids[r, 0..max_gen_len) != -1)
+ *   out[r, :] = sample_hidden[(gen_len - 1) + row_offsets[r], :]
+ * row_offsets [num_requests] int64 (device) = exclusive cumsum of (num_draft_tokens + 1).
+ * One launch instead of ne / sum / cumsum / sub / add / index. */
+AB200_API int32_t ab200_select_hidden_rows(const void* sample_hidden, int64_t hidden_row_stride_bytes,
+                                           int64_t num_hidden_rows, const int64_t* sampled_token_ids,
+                                           int64_t sampled_row_stride, int32_t max_gen_len,
+                                           const int64_t* row_offsets, int64_t num_requests, void* out,
+                                           int64_t out_row_stride_bytes, int64_t row_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Arctic MLP speculator / "sum_rnn" step - SURVEY 8f "next" rank 3.
  * Replaces: ArcticMLPSpeculator.generate_states (arctic_speculator.py:265-285) and the sum_rnn
