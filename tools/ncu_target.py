@@ -21,3 +21,11 @@ torch.cuda.synchronize()
 print("tokens", out[0].tolist())
 kv = bench.bench_kv_write(dev, iters=3, peak_gbs=6557.1)
 print("kv GB/s", kv["value"])
+# round-1 additions: the fused cell in its HBM-bound regime, the FP8 KV write, the MLP speculator step
+cell = bench.bench_cell_hbm_regime(dev, 6557.1, iters=1)
+print("cell 16384 rows: exact %.0f GB/s, faithful %.0f GB/s" % (cell["exact"]["gbs"], cell["faithful"]["gbs"]))
+from arcticinference_b200.mlp_speculator import ArcticMLPSpeculator
+mlp = ArcticMLPSpeculator(vocab_size=V, emb_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=dev, enforce_eager=True)
+bench.synthetic_weights(mlp, 1)
+print("mlp tokens", mlp.generate_proposals(ids, hid, S)[0].tolist())
+torch.cuda.synchronize()
