@@ -498,7 +498,11 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
         gelu_lut_init_kernel<<<1, kGeluLutSize, 0, s>>>();
         AB200_CHECK_LAUNCH("gelu_lut_init_kernel");
         lc.cfg.numAttrs = 0;
-        if (dev >= 0 && dev < 64) lut_ready[dev] = true;
+        // under stream capture the fill only runs when the graph is replayed: keep filling until an
+        // eager launch has really executed it
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        (void)cudaStreamIsCapturing(s, &cap);
+        if (dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone) lut_ready[dev] = true;
       }
       // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
       // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM

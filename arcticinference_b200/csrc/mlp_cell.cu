@@ -262,7 +262,11 @@ static int launch_mlp(const void* pre, int64_t ldp, const void* emb, const int64
         gelu_lut_init_mlp_kernel<<<1, kGeluLutSize, 0, s>>>();
         AB200_CHECK_LAUNCH("gelu_lut_init_mlp_kernel");
         lc.cfg.numAttrs = 0;   // this launch reads the table before its dependency wait
-        if (dev >= 0 && dev < 64) lut_ready[dev] = true;
+        // under stream capture the fill only runs when the graph is replayed: keep filling until an
+        // eager launch has really executed it
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        (void)cudaStreamIsCapturing(s, &cap);
+        if (dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone) lut_ready[dev] = true;
       }
 #define AB200_MLP_FAST(IT)                                                                     \
   do {                                                                                         \
