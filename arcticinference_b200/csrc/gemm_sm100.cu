@@ -468,6 +468,276 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   if (threadIdx.x == 0) trace_stamp(p.trace, 2);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) for 129..256 batch rows per pass.
+//
+// Two CTAs of one cluster (the two SMs of a TPC) execute ONE UMMA of M = 256 x N = block_n:
+// CTA r holds batch rows [128 r, 128 r + 128) of x and the accumulators of those rows in its own
+// TMEM, and HALF of the weight tile (block_n / 2 rows) in its shared memory; the tensor cores of
+// both SMs read both halves.  Per output element an SM therefore ingests 1.0 byte from L2 instead
+// of the 1.5 bytes of the single-CTA MT = 2 shape - that ingest (13.9 TB/s aggregate at B = 256),
+// not HBM or the tensor pipe, is what bounds the single-CTA kernel above 128 rows.
+//
+// Protocol (after CUTLASS' 2-SM pipelines): the stage-full barrier lives in the leader CTA (rank 0)
+// and counts the TMA bytes of BOTH CTAs (cp.async.bulk.tensor.cta_group::2 with the peer bit of the
+// barrier address cleared); only the leader issues tcgen05.mma.cta_group::2; tcgen05.commit with
+// .multicast::cluster releases the shared-memory stage / publishes the accumulators in both CTAs;
+// the epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on rank 0's barrier at this offset
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
+                                                int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_2sm_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const GemmParams p) {
+  constexpr int kAcc = 256;   // TMEM columns per accumulator buffer (block_n <= 256), two buffers
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = static_cast<int>(blockIdx.x >> 1), npairs = static_cast<int>(gridDim.x >> 1);
+  const int stages = p.stages;
+  const int half_n = p.block_n >> 1;
+  const uint32_t b_bytes = static_cast<uint32_t>(half_n) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                      // used in the leader only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };          // one per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * stages + a); };      // one per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * stages + 2 + a); }; // used in the leader only
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const uint32_t flag_slot = tmem_slot + 8u;
+
+  if (warp == 0 && lane == 0) {
+    trace_stamp(p.trace, 0);
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 8);   // 4 epilogue warps x 2 CTAs
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (!p.late_trigger) pdl_launch_dependents();
+
+  const int num_kb = p.num_k_blocks;
+  const int my_tiles = pair < p.num_n_tiles ? (p.num_n_tiles - 1 - pair) / npairs + 1 : 0;
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const int total = my_tiles * num_kb;
+      auto n0_of = [&](int g) { return (pair + (g / num_kb) * npairs) * p.block_n + static_cast<int>(rank) * half_n; };
+      auto load_x = [&](int g, int stage) {
+        tma_load_2d_2sm(smem_base + stage * stage_bytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK,
+                        static_cast<int>(rank) * kTileM, kEvictLast);
+      };
+      auto load_w = [&](int g, int stage) {
+        tma_load_2d_2sm(smem_base + stage * stage_bytes + kABytes, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK,
+                        n0_of(g), kEvictFirst);
+      };
+      const int pre = total < p.pre_stages ? total : p.pre_stages;
+      for (int g = 0; g < pre; ++g) {
+        if (rank == 0) mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
+        load_w(g, g);
+      }
+      pdl_wait();
+      trace_stamp(p.trace, 1);
+      for (int g = 0; g < pre; ++g) load_x(g, g);
+      int stage = pre == stages ? 0 : pre;
+      uint32_t phase = pre == stages ? 1u : 0u;
+      for (int g = pre; g < total; ++g) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+        load_x(g, stage);
+        load_w(g, stage);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      if (p.late_trigger) pdl_launch_dependents();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // both CTAs' epilogues have drained this buffer
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);          // the bytes of both CTAs have landed
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint64_t da = smem_desc_sw128(sa);
+            const uint64_t db = smem_desc_sw128(sa + kABytes);
+            const uint32_t tmem_d = tmem_base + acc * kAcc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_2sm_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int quad = warp & 3;
+    const int row = static_cast<int>(rank) * kTileM + quad * 32 + lane;   // batch row of this thread
+    const bool row_ok = row < p.m_rows;
+    const bool warp_has_rows = static_cast<int>(rank) * kTileM + quad * 32 < p.m_rows;
+    float best = -INFINITY;
+    uint32_t best_idx = 0xFFFFFFFFu;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int n0 = (pair + it * npairs) * p.block_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAcc;
+      if (warp_has_rows) {
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c0;
+          if constexpr (EPI == EPI_STORE) {
+            if (row_ok && col0 < p.n_valid) {
+              __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + col0;
+              if (col0 + 16 <= p.n_valid) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                  w[j] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              } else {
+                for (int j = 0; j < 16 && col0 + j < p.n_valid; ++j) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+              }
+            }
+          } else {
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float v = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[j])));
+                const int col = col0 + j;
+                if (col < p.n_valid && v > best) {
+                  best = v;
+                  best_idx = static_cast<uint32_t>(col);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+    }
+    if constexpr (EPI == EPI_ARGMAX) {
+      if (row_ok && best_idx != 0xFFFFFFFFu) atomicMax(p.packed + row, pack_arg(best, best_idx));
+      if (p.tokens_out != nullptr) {
+        const int et = threadIdx.x - 64;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const unsigned int prev = atomicAdd(p.done_counter, 1u);
+          const uint32_t last = prev == gridDim.x - 1 ? 1u : 0u;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag_slot), "r"(last) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t last;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag_slot) : "memory");
+        if (last) {
+          __threadfence();
+          for (int r = et; r < p.m_rows; r += 128) {
+            const unsigned long long pk = *reinterpret_cast<volatile unsigned long long*>(p.packed + r);
+            p.tokens_out[static_cast<int64_t>(r) * p.tokens_stride] = static_cast<int64_t>(unpack_idx(pk));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves (and frees its barriers / TMEM) while its peer may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+  if (threadIdx.x == 0) trace_stamp(p.trace, 2);
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -630,6 +900,74 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   return AB200_OK;
 }
 
+
+// 129..256 rows: the CTA-pair kernel (see gemm_tn_sm100_2cta)
+template <int EPI>
+static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
+                                 int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out, int64_t ldo,
+                                 const ArgmaxExtra& ax, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100_2cta<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemLimit));
+    attr_set = true;
+  }
+  const int pairs = sm_count() / 2;
+  // tile width: multiple of 32 (each CTA holds half of it), balanced over the CTA pairs
+  int bn = 32;
+  double best_cost = 1e30;
+  for (int c = 32; c <= 256; c += 32) {
+    const int64_t tiles = (n_valid + c - 1) / c;
+    const int64_t waves = (tiles + pairs - 1) / pairs;
+    const double cost = static_cast<double>(waves) * (c + 16.0);
+    if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && c > bn)) {
+      best_cost = cost;
+      bn = c;
+    }
+  }
+  const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
+  const uint32_t stage_bytes = kABytes + (bn / 2) * 128;
+  int stages = (kSmemLimit - 1024 - 256) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
+  CUtensorMap tmx, tmw;
+  int rc = make_tmap(&tmx, x, m_rows, K, ldx, kTileM, 2);
+  if (rc != AB200_OK) return rc;
+  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2);
+  if (rc != AB200_OK) return rc;
+  GemmParams p;
+  p.m_rows = static_cast<int32_t>(m_rows);
+  p.n_valid = static_cast<int32_t>(n_valid);
+  p.block_n = bn;
+  p.num_n_tiles = num_n_tiles;
+  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
+  p.stages = stages;
+  p.l2_prefetch_kb = 0;
+  p.late_trigger = env_int("AB200_LATE_TRIGGER", 1);
+  p.pre_stages = env_int("AB200_PRE_STAGES", stages);
+  if (p.pre_stages > stages) p.pre_stages = stages;
+  if (p.pre_stages < 0) p.pre_stages = 0;
+  p.m64 = 0;
+  p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u);   // both CTAs
+  // instruction descriptor: D = f32, A/B = bf16, K-major, N >> 3, M = 256 >> 4
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (16u << 24);
+  p.x_scales = nullptr;
+  p.w_scale = nullptr;
+  p.out = out;
+  p.ldo = ldo;
+  p.packed = ax.packed;
+  p.tokens_out = ax.tokens_out;
+  p.tokens_stride = ax.tokens_stride;
+  p.done_counter = ax.done_counter;
+  p.trace = next_trace_slot();
+  const int use_pairs = num_n_tiles < pairs ? num_n_tiles : pairs;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+  LaunchCfg cfg(dim3(2 * use_pairs), dim3(kGemmThreads), smem, s);
+  AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_tn_sm100_2cta<EPI>, tmx, tmw, p));
+  AB200_CHECK_LAUNCH("gemm_tn_sm100_2cta");
+  return AB200_OK;
+}
+
 template <int EPI, int KIND = KIND_BF16>
 static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
@@ -657,6 +995,8 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
     int rc;
     if (rows <= kTileM)
       rc = launch_gemm_pass<EPI, 1, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
+    else if (rows <= 2 * kTileM && KIND == KIND_BF16 && env_int("AB200_GEMM_2CTA", 1))
+      rc = launch_gemm_pass_2cta<EPI>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else if (rows <= 2 * kTileM)
       rc = launch_gemm_pass<EPI, 2, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else

@@ -196,6 +196,8 @@ def main():
     only = set(a.only.split(",")) if a.only else None
     if not only or "gemm" in only:
         sweep_gemm(rows, 128256, 4096, 4096, [1, 8, 32, 64, 128, 256, 512], [1, 8, 16, 32])
+    if only and "gemmbig" in only:
+        sweep_gemm(rows, 128256, 4096, 4096, [160, 192, 256, 384, 512], [])
     if not only or "gemm70" in only:
         sweep_gemm(rows, 128256, 8192, 8192, [64, 128, 256], [32])
     if not only or "gemmoss" in only:
