@@ -82,6 +82,7 @@ SIGNATURES = {
     "ab200_head_argmax_fp8": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                         c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                         c_int64, c_void_p, c_void_p]),
+    "ab200_argmax_shard_key": (c_int32, [c_void_p, c_int64, c_int64, c_void_p]),
     "ab200_argmax_unpack": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "ab200_argmax_rows": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p,
                                     c_void_p]),

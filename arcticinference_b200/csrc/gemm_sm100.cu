@@ -1213,6 +1213,32 @@ extern "C" int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, 
   return ab200_argmax_unpack(packed_out, tokens_out, M, tokens_stride, stream);
 }
 
+// Tensor-parallel (vocab-sharded) head: turn a shard-local packed arg-max into a key that a plain
+// signed 64-bit MAX all-reduce combines correctly - global token index, order-preserving for int64.
+// Replaces the topk / pack-as-f64 / all_gather / argmax / gather sequence of
+// arctic_speculator.py:733-744 by one kernel + one all_reduce(MAX).
+__global__ void argmax_shard_key_kernel(unsigned long long* __restrict__ packed, int64_t count,
+                                        uint32_t index_offset) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  unsigned long long p = packed[i];
+  if (p != 0ull) {   // 0 = this shard found nothing: stays the smallest key
+    const uint32_t gidx = unpack_idx(p) + index_offset;
+    p = (p & 0xFFFFFFFF00000000ull) | static_cast<unsigned long long>(0xFFFFFFFFu - gidx);
+  }
+  packed[i] = p ^ 0x8000000000000000ull;   // unsigned order -> signed order
+}
+
+extern "C" int32_t ab200_argmax_shard_key(uint64_t* packed, int64_t count, int64_t index_offset, void* stream) {
+  if (count == 0) return AB200_OK;
+  AB200_REQUIRE(packed && count > 0 && index_offset >= 0 && index_offset < (1LL << 31), AB200_E_INVALID,
+                "argmax_shard_key: bad arguments");
+  argmax_shard_key_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long*>(packed), count, static_cast<uint32_t>(index_offset));
+  AB200_CHECK_LAUNCH("argmax_shard_key_kernel");
+  return AB200_OK;
+}
+
 extern "C" int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
                                        int64_t out_stride, void* stream) {
   if (count == 0) return AB200_OK;

@@ -54,3 +54,28 @@ def aggregate(elapsed_ms: float, units: float, device: torch.device | str = "cpu
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), float(u.item())
+
+
+# ---- tensor-parallel head: host mirror of the arg-max key format (csrc/common.cuh pack_arg,
+# gemm_sm100.cu argmax_shard_key_kernel) - used by the CPU tests of the all-reduce plumbing ----------
+def pack_argmax_key(logit: float, local_index: int, index_offset: int = 0) -> int:
+    """Signed 64-bit key of (logit, global index): larger logit wins, equal logits -> lower index."""
+    import struct
+    v = logit + 0.0
+    u = struct.unpack("<I", struct.pack("<f", v))[0]
+    order = (~u & 0xFFFFFFFF) if (u & 0x80000000) else (u | 0x80000000)
+    p = (order << 32) | (0xFFFFFFFF - (local_index + index_offset))
+    p ^= 0x8000000000000000
+    return p - (1 << 64) if p >= (1 << 63) else p
+
+
+def unpack_argmax_key(key: int) -> int:
+    return 0xFFFFFFFF - (key & 0xFFFFFFFF)
+
+
+def all_reduce_argmax_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
+    """One MAX all-reduce over int64 keys = the reference's topk + all_gather + argmax + gather
+    (arctic_speculator.py:733-744)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    return keys

@@ -59,8 +59,15 @@ class ArcticLSTMSpeculator:
                  dtype: torch.dtype = torch.bfloat16, device: str | torch.device = "cuda",
                  scale_input: bool = True, enforce_eager: bool = False,
                  emulate_eager_rounding: bool | int = True, alpha_flavor: str = "cuda",
-                 quantize_lm_head: bool = False, fp8_head_max_batch: int = 32) -> None:
+                 quantize_lm_head: bool = False, fp8_head_max_batch: int = 32,
+                 tp_size: int = 1, tp_rank: int = 0, tp_group=None) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
+        # Tensor parallelism of the vocab head (the reference shards ParallelLMHead over
+        # max(TP, SP) ranks, vocab_parallel_embedding.py:20-35, and merges local top-1s with an
+        # all_gather, arctic_speculator.py:733-744).  Everything else is replicated.
+        if tp_size < 1 or not 0 <= tp_rank < tp_size:
+            raise ValueError("bad tp_size / tp_rank")
+        self.tp_size, self.tp_rank, self.tp_group = tp_size, tp_rank, tp_group
         if dtype not in (torch.bfloat16, torch.float32):
             raise ValueError("dtype must be torch.bfloat16 or torch.float32")
         if inner_dim % 8 or input_hidden_dim % 8:
@@ -104,9 +111,15 @@ class ArcticLSTMSpeculator:
 
         D, H, V = inner_dim, input_hidden_dim, vocab_size
         Vp = pad_vocab_size(V)
+        if Vp % tp_size:
+            raise ValueError("padded vocab size must be divisible by tp_size")
+        self.vocab_padded = Vp
+        self.vocab_per_rank = Vp // tp_size          # num_embeddings_per_partition
+        if tp_size > 1 and quantize_lm_head:
+            raise ValueError("the FP8 head is not built for tp_size > 1")
         mk = lambda *shape: torch.zeros(*shape, dtype=dtype, device=self.device)
         self._params: Dict[str, torch.Tensor] = collections.OrderedDict([
-            ("head.0.weight", mk(Vp, D)),
+            ("head.0.weight", mk(self.vocab_per_rank, D)),
             ("forget_emb.0.weight", mk(V, D)),
             ("projs.0.weight", mk(4 * D, H)),
             ("projs.1.weight", mk(4 * D, D)),
@@ -134,6 +147,13 @@ class ArcticLSTMSpeculator:
 
     def _set_param(self, name: str, value: torch.Tensor) -> None:
         p = self._params[name]
+        if name.startswith("head") and self.tp_size > 1 and value.shape[0] != p.shape[0]:
+            # full (unsharded) head given: keep this rank's vocab partition
+            lo = self.tp_rank * self.vocab_per_rank
+            part = value[lo:lo + self.vocab_per_rank]
+            p.zero_()
+            p[:part.shape[0]].copy_(part)
+            return
         if tuple(p.shape) != tuple(value.shape):
             if name.startswith("head") and value.shape[0] <= p.shape[0] and value.shape[1:] == p.shape[1:]:
                 p.zero_()                       # vocab-padding rows stay zero
@@ -275,6 +295,13 @@ class ArcticLSTMSpeculator:
     def greedy_tokens(self, states: torch.Tensor) -> torch.Tensor:
         """Head projection + arg-max for states [B, D] (logits_processor_opt.py:83-107,
         arctic_speculator.py:726-732) -> [B] int64."""
+        if self.tp_size > 1:
+            keys = self._all_reduce_max(self.local_argmax_keys(states), states)
+            toks = torch.empty(states.shape[0], dtype=torch.long, device=self.device)
+            with torch.cuda.device(self.device):
+                _capi.check(self._lib.ab200_argmax_unpack(keys.data_ptr(), toks.data_ptr(), states.shape[0], 1,
+                                                          _capi.current_stream_ptr(self.device)), "ab200_argmax_unpack")
+            return toks
         lib, head = self._lib, self._params["head.0.weight"]
         B, D = states.shape
         states = states.contiguous()
@@ -293,6 +320,53 @@ class ArcticLSTMSpeculator:
                                               ws.data_ptr() if ws is not None else None,
                                               ws.numel() * 4 if ws is not None else 0, stream),
                         "ab200_head_argmax")
+        return out
+
+    # ---- tensor-parallel head -----------------------------------------------------------------
+    def local_argmax_keys(self, states: torch.Tensor) -> torch.Tensor:
+        """Arg-max of this rank's vocab partition as all-reduce keys [B] int64 (global token index,
+        signed order = (logit, lowest index) order).  Like the reference (:733-736, logits are only
+        cut at org_vocab_size) the partition's zero-weight padding rows take part."""
+        lib, head = self._lib, self._params["head.0.weight"]
+        B, D = states.shape
+        states = states.contiguous()
+        packed = torch.zeros(B, dtype=torch.int64, device=self.device)
+        code = _capi.torch_dtype_code(self.dtype)
+        per = self.vocab_per_rank
+        n_valid = per                                      # the whole partition
+        ws = torch.empty(B * n_valid, dtype=torch.float32, device=self.device) if self.dtype == torch.float32 else None
+        stream = _capi.current_stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _capi.check(lib.ab200_head_argmax(states.data_ptr(), head.data_ptr(), B, head.shape[0], D, n_valid,
+                                              states.stride(0), head.stride(0), packed.data_ptr(), None, 0, None,
+                                              code, ws.data_ptr() if ws is not None else None,
+                                              ws.numel() * 4 if ws is not None else 0, stream), "ab200_head_argmax")
+            _capi.check(lib.ab200_argmax_shard_key(packed.data_ptr(), B, self.tp_rank * per, stream),
+                        "ab200_argmax_shard_key")
+        return packed
+
+    def _all_reduce_max(self, keys: torch.Tensor, states: torch.Tensor) -> torch.Tensor:
+        g = self.tp_group
+        if hasattr(g, "all_reduce_max"):           # test double: see tests/test_tp_gpu.py
+            return g.all_reduce_max(keys, states)
+        import torch.distributed as dist
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=g)
+        return keys
+
+    def _propose_tp(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor, B: int, S: int) -> torch.Tensor:
+        """generate_token_ids with tp_size > 1 (arctic_speculator.py:706-751, branch :733-744): one MAX
+        all-reduce of [B] int64 keys per step instead of topk + all_gather of [2B,1] + argmax + gather."""
+        tokens = input_ids.to(device=self.device, dtype=torch.long).reshape(B, 1)
+        prev = previous_hidden_states.to(device=self.device, dtype=self.dtype).reshape(B, 1, -1)
+        cell = None
+        out = torch.empty(B, S, dtype=torch.long, device=self.device)
+        for s in range(S):
+            state, cell = self.generate_states(tokens, prev, s, cell)
+            keys = self._all_reduce_max(self.local_argmax_keys(state.reshape(B, -1)), state.reshape(B, -1))
+            with torch.cuda.device(self.device):
+                _capi.check(self._lib.ab200_argmax_unpack(keys.data_ptr(), out[:, s].data_ptr(), B, S,
+                                                          _capi.current_stream_ptr(self.device)), "ab200_argmax_unpack")
+            tokens, prev = out[:, s:s + 1], state
         return out
 
     def generate_token_ids(self, batch_size: int, num_predict_tokens: int, last_tokens: torch.Tensor,
@@ -325,6 +399,8 @@ class ArcticLSTMSpeculator:
             return torch.empty(0, S, dtype=torch.long, device=self.device)
         if previous_hidden_states.shape != (B, self.input_hidden_dim):
             raise RuntimeError(f"previous_hidden_states must be [{B}, {self.input_hidden_dim}]")
+        if self.tp_size > 1:
+            return self._propose_tp(input_ids, previous_hidden_states, B, S)
         use_graph = self.cuda_graph_mode and B <= self.cuda_graph_max_batch_size
         if not use_graph:
             ids = input_ids.to(device=self.device, dtype=torch.long).contiguous()

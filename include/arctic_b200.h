@@ -217,6 +217,12 @@ AB200_API int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, c
 AB200_API int32_t ab200_argmax_unpack(const uint64_t* packed, int64_t* tokens_out, int64_t count,
                             int64_t out_stride, void* stream);
 
+/* Tensor-parallel head (vocab sharded over ranks, arctic_speculator.py:733-744): rewrites a shard-local
+ * packed arg-max in place into a key with the GLOBAL token index (local + index_offset) whose signed
+ * 64-bit order equals (logit, lowest index) order, so that ONE all_reduce(MAX) over int64 combines
+ * the ranks; ab200_argmax_unpack and the cell kernels read such keys like ordinary packed values. */
+AB200_API int32_t ab200_argmax_shard_key(uint64_t* packed, int64_t count, int64_t index_offset, void* stream);
+
 /* Row-wise argmax over materialised logits [M, N] (lowest index on ties) into the packed format.
  * Used by the f32 path and by tests. packed_out need not be zeroed. */
 AB200_API int32_t ab200_argmax_rows(const void* logits, int64_t M, int64_t N, int64_t ld, int32_t dtype,
