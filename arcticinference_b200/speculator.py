@@ -19,9 +19,11 @@ Everything numeric runs in libarctic_b200.so (hand-written sm_100a kernels) thro
 PyTorch only owns device memory, the stream and the CUDA-graph capture.  There is no PyTorch or
 CPU fallback: without the native library construction raises.
 
-Only ``method="sum_lstm"`` with ``tie_weights`` / ``tie_lstm_embs`` (the configuration the
-reference's hot path asserts, :545, :663), TP = 1 and the unquantised head are built; the FP8
-``qhead`` (batch <= 32, :726-727) is out of scope (arithmetic lives in vllm 0.9.2).
+Built: ``method="sum_lstm"`` with ``tie_weights`` / ``tie_lstm_embs`` (the configuration the
+reference's hot path asserts, :545, :663); the FP8 ``qhead`` for padded batches <= 32 (:726-727)
+as an option (``quantize_lm_head=True``; pinned against vLLM 0.22's fp8 ops); a
+vocab-sharded head for ``tp_size > 1`` (:733-744) whose per-step exchange is one MAX all-reduce.
+``method="sum_rnn"`` / ``ArcticMLPSpeculator`` live in ``mlp_speculator.py``.
 """
 from __future__ import annotations
 
