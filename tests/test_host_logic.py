@@ -1,0 +1,93 @@
+"""CPU: host-side logic that needs no GPU - batch padding rule, parameter layouts of the speculator
+mirrors, weight-index rules, argument validation of the no-fallback entry points."""
+import numpy as np
+import pytest
+import torch
+
+from arcticinference_b200 import _capi
+from arcticinference_b200.speculator import pad_vocab_size, padding_size
+from oracle import speculator_ref as O
+
+
+def test_padding_size_matches_reference_rule():
+    # arctic_speculator.py:39-44: multiples of pow2ceil(size)//4
+    expect = {1: 1, 2: 2, 3: 3, 4: 4, 5: 6, 6: 6, 7: 8, 8: 8, 9: 12, 13: 16, 17: 24, 25: 32, 33: 48, 49: 64, 64: 64,
+              65: 96, 100: 128, 129: 192, 200: 256, 257: 384, 512: 512}
+    for size, padded in expect.items():
+        assert padding_size(size) == padded == O.padding_size(size)
+    for size in range(1, 600):
+        p = padding_size(size)
+        assert p >= size and p < 2 * size + 1
+
+
+def test_pad_vocab_size():
+    assert pad_vocab_size(128256) == 128256 and pad_vocab_size(201088) == 201088
+    assert pad_vocab_size(1000) == 1024 and pad_vocab_size(2051) == 2112 and pad_vocab_size(64) == 64
+
+
+def test_ctypes_struct_layouts_match_the_header():
+    # struct sizes as a C compiler lays them out (include/arctic_b200.h)
+    import ctypes
+    assert ctypes.sizeof(_capi.LstmSpeculatorDesc) == 8 + 4 * 8 + 16 + 8 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_capi.MlpSpeculatorDesc) == 8 + 4 * 8 + 16 + 7 * 8 * _capi.AB200_MLP_MAX_STAGES + 8
+    assert _capi.LstmSpeculatorDesc.head.offset % 8 == 0 and _capi.MlpSpeculatorDesc.emb.offset % 8 == 0
+
+
+def test_no_cpu_fallback_anywhere():
+    """CPU tensors must be refused, not silently computed elsewhere."""
+    from arcticinference_b200 import py_custom_ops, swiftkv
+    assert py_custom_ops.try_load_torch_library()
+    k = torch.zeros(4, 32, dtype=torch.bfloat16)
+    c = torch.zeros(2, 2, 4, 2, 8, dtype=torch.bfloat16)
+    s = [torch.ones(())]
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        py_custom_ops.reshape_and_cache_flash_bulk(k, k, [c[0]], [c[1]], torch.zeros(4, dtype=torch.long), "auto", s, s, 2, 8)
+    with pytest.raises(NotImplementedError):
+        swiftkv.gather_rows([k], torch.zeros(2, dtype=torch.long))
+
+
+def test_speculator_constructors_validate_without_gpu():
+    from arcticinference_b200.mlp_speculator import ArcticMLPSpeculator
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    with pytest.raises(ValueError):
+        ArcticLSTMSpeculator(vocab_size=100, input_hidden_dim=30, inner_dim=32, n_predict=3, device="cpu")     # H % 8
+    with pytest.raises(ValueError):
+        ArcticLSTMSpeculator(vocab_size=100, input_hidden_dim=32, inner_dim=32, n_predict=3, device="cpu", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        ArcticLSTMSpeculator(vocab_size=100, input_hidden_dim=32, inner_dim=32, n_predict=3, device="cpu", tp_size=3)  # 128 % 3
+    with pytest.raises(AssertionError):
+        ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=32, n_predict=1, tie_weights=True, device="cpu")
+    with pytest.raises(ValueError):
+        ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=32, n_predict=9, tie_weights=False, device="cpu")
+
+
+def test_mlp_parameter_names_and_index_rule():
+    from arcticinference_b200.mlp_speculator import ArcticMLPSpeculator
+    tied = ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=16, n_predict=4, tie_weights=True, device="cpu")
+    assert [n for n, _ in tied.named_parameters()] == ["emb.0.weight", "proj.0.weight", "proj.1.weight", "head.0.weight",
+                                                       "ln.0.weight", "ln.0.bias"]
+    shapes = dict((n, tuple(p.shape)) for n, p in tied.named_parameters())
+    assert shapes["emb.0.weight"] == (128, 16) and shapes["proj.0.weight"] == (16, 32) and shapes["proj.1.weight"] == (16, 16)
+    assert [tied._idx(s) for s in range(4)] == [0, 0, 0, 0] and [tied._idx(s, True) for s in range(4)] == [0, 1, 1, 1]
+    untied = ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=16, n_predict=3, tie_weights=False, device="cpu")
+    assert len(untied.named_parameters()) == 3 * 5
+    assert [untied._idx(s, True) for s in range(3)] == [0, 1, 2]
+
+
+def test_lstm_parameter_layout_and_tp_partition():
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    m = ArcticLSTMSpeculator(vocab_size=1000, input_hidden_dim=48, inner_dim=32, n_predict=3, device="cpu")
+    shapes = dict((n, tuple(p.shape)) for n, p in m.named_parameters())
+    assert shapes == {"head.0.weight": (1024, 32), "forget_emb.0.weight": (1000, 32), "projs.0.weight": (128, 48),
+                      "projs.1.weight": (128, 32), "cell_ln.0.weight": (32,), "cell_ln.0.bias": (32,),
+                      "state_ln.0.weight": (32,), "state_ln.0.bias": (32,)}
+    r1 = ArcticLSTMSpeculator(vocab_size=1000, input_hidden_dim=48, inner_dim=32, n_predict=3, device="cpu", tp_size=4, tp_rank=1)
+    assert dict(r1.named_parameters())["head.0.weight"].shape == (256, 32)
+    full = torch.arange(1024 * 32, dtype=torch.float32).reshape(1024, 32).to(torch.bfloat16)
+    r1.load_weights([("head.0.weight", full)])
+    assert torch.equal(dict(r1.named_parameters())["head.0.weight"], full[256:512])
+    # raw checkpoints: gate projections fused in the order f, i, o, c (arctic_speculator.py:878-892)
+    parts = {f"{g}_proj.1.weight": torch.full((32, 32), float(i)) for i, g in enumerate(("forget", "input", "output", "cell"))}
+    m.load_weights(list(parts.items()) + [("input_emb.0.weight", torch.zeros(1))])
+    w = dict(m.named_parameters())["projs.1.weight"].float()
+    assert [w[i * 32, 0].item() for i in range(4)] == [0.0, 1.0, 2.0, 3.0]
