@@ -120,6 +120,14 @@ __device__ __forceinline__ uint4 ld_stream_16(const void* p) {
                : "l"(p));
   return r;
 }
+// plain (coherent) 16-byte load as volatile asm: keeps its place among the other volatile loads
+__device__ __forceinline__ uint4 ld_ordered_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_stream_16(void* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)

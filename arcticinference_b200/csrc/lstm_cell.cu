@@ -262,11 +262,13 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
     if (clear_packed) clear_packed[row] = 0ull;
     if (clear_counter && row == 0) *clear_counter = 0u;
   }
+  // Latency variant (small batches, one CTA per SM): the LayerNorm vectors are fetched up front
+  // instead of after each row reduction, so that their L2 latency is off the critical path.
+  constexpr bool PRE = MAXT == 512 && MINB == 1;
   int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
-  if (static_cast<uint64_t>(tok) >= static_cast<uint64_t>(vocab)) tok = tok < 0 ? 0 : vocab - 1;
 
   const T* g = gates + row * ldg;
-  const T* z = emb + tok * static_cast<int64_t>(D);
+  uint4 lnw1[PRE ? ITEMS : 1], lnb1[PRE ? ITEMS : 1], lnw2[PRE ? ITEMS : 1], lnb2[PRE ? ITEMS : 1];
 
   uint32_t F[ITEMS][4], I[ITEMS][4], O[ITEMS][4], CC[ITEMS][4], C[ITEMS][4];
   float ss = 0.f;
@@ -278,9 +280,22 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
       const uint4 gi = ld_stream_16(g + 1 * D + vi * 8);
       const uint4 go = ld_stream_16(g + 2 * D + vi * 8);
       const uint4 gc = ld_stream_16(g + 3 * D + vi * 8);
-      const uint4 ze = *reinterpret_cast<const uint4*>(z + vi * 8);
       uint4 cp = make_uint4(0u, 0u, 0u, 0u);
-      if (cell_prev) cp = *reinterpret_cast<const uint4*>(cell_prev + row * D + vi * 8);
+      if constexpr (PRE) {
+        if (cell_prev) cp = ld_ordered_16(cell_prev + row * D + vi * 8);
+        lnw1[it] = ld_ordered_16(wc + vi * 8);
+        lnb1[it] = ld_ordered_16(bc + vi * 8);
+        lnw2[it] = ld_ordered_16(ws + vi * 8);
+        lnb2[it] = ld_ordered_16(bs + vi * 8);
+      } else {
+        if (cell_prev) cp = *reinterpret_cast<const uint4*>(cell_prev + row * D + vi * 8);
+      }
+      // everything that does not depend on the token is in flight before the token is consumed
+      // (the embedding row is the only load behind the token's L2 round trip)
+      asm volatile("" : "+l"(tok));
+      int64_t tk = tok;
+      if (static_cast<uint64_t>(tk) >= static_cast<uint64_t>(vocab)) tk = tk < 0 ? 0 : vocab - 1;
+      const uint4 ze = ld_stream_16(emb + tk * static_cast<int64_t>(D) + vi * 8);
       const uint32_t gfa[4] = {gf.x, gf.y, gf.z, gf.w}, gia[4] = {gi.x, gi.y, gi.z, gi.w};
       const uint32_t goa[4] = {go.x, go.y, go.z, go.w}, gca[4] = {gc.x, gc.y, gc.z, gc.w};
       const uint32_t zea[4] = {ze.x, ze.y, ze.z, ze.w}, cpa[4] = {cp.x, cp.y, cp.z, cp.w};
@@ -314,8 +329,14 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
     for (int it = 0; it < ITEMS; ++it) {
       const int vi = threadIdx.x + it * blockDim.x;
       if (FULL || vi < nvec) {
-        const uint4 w = *reinterpret_cast<const uint4*>(wc + vi * 8);
-        const uint4 b = *reinterpret_cast<const uint4*>(bc + vi * 8);
+        uint4 w, b;
+        if constexpr (PRE) {
+          w = lnw1[it];
+          b = lnb1[it];
+        } else {
+          w = *reinterpret_cast<const uint4*>(wc + vi * 8);
+          b = *reinterpret_cast<const uint4*>(bc + vi * 8);
+        }
         const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -344,8 +365,14 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
     for (int it = 0; it < ITEMS; ++it) {
       const int vi = threadIdx.x + it * blockDim.x;
       if (FULL || vi < nvec) {
-        const uint4 w = *reinterpret_cast<const uint4*>(ws + vi * 8);
-        const uint4 b = *reinterpret_cast<const uint4*>(bs + vi * 8);
+        uint4 w, b;
+        if constexpr (PRE) {
+          w = lnw2[it];
+          b = lnb2[it];
+        } else {
+          w = *reinterpret_cast<const uint4*>(ws + vi * 8);
+          b = *reinterpret_cast<const uint4*>(bs + vi * 8);
+        }
         const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -530,7 +557,8 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       if (B >= 4096 && items == 1 && threads % 64 == 0 && threads >= 128 && threads <= 512) {
         lc.cfg.blockDim = dim3(threads / 2);
         AB200_FAST_LAUNCH(2, 256, 4);
-      } else if (items == 1 && threads <= 512) AB200_FAST_LAUNCH(1, 512, 3);
+      } else if (items == 1 && threads <= 512 && B <= 1024) AB200_FAST_LAUNCH(1, 512, 1);   // latency variant
+      else if (items == 1 && threads <= 512) AB200_FAST_LAUNCH(1, 512, 3);
       else if (items == 1) AB200_FAST_LAUNCH(1, 1024, 1);
       else if (items == 2) AB200_FAST_LAUNCH(2, 1024, 1);
       else AB200_FAST_LAUNCH(4, 1024, 1);
