@@ -262,7 +262,7 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
     if (clear_packed) clear_packed[row] = 0ull;
     if (clear_counter && row == 0) *clear_counter = 0u;
   }
-  // Latency variant (small batches, one CTA per SM): the LayerNorm vectors are fetched up front
+  // Latency variant (batches of at most ~one CTA per SM): the LayerNorm vectors are fetched up front
   // instead of after each row reduction, so that their L2 latency is off the critical path.
   constexpr bool PRE = MAXT == 512 && MINB == 1;
   int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
@@ -557,7 +557,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       if (B >= 4096 && items == 1 && threads % 64 == 0 && threads >= 128 && threads <= 512) {
         lc.cfg.blockDim = dim3(threads / 2);
         AB200_FAST_LAUNCH(2, 256, 4);
-      } else if (items == 1 && threads <= 512 && B <= 1024) AB200_FAST_LAUNCH(1, 512, 1);   // latency variant
+      } else if (items == 1 && threads <= 512 && B <= 160) AB200_FAST_LAUNCH(1, 512, 1);   // latency variant: <= 1 CTA per SM anyway
       else if (items == 1 && threads <= 512) AB200_FAST_LAUNCH(1, 512, 3);
       else if (items == 1) AB200_FAST_LAUNCH(1, 1024, 1);
       else if (items == 2) AB200_FAST_LAUNCH(2, 1024, 1);
