@@ -285,8 +285,10 @@ class ArcticMLPSpeculator:
     def _replay(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor, B: int,
                 S: int) -> torch.Tensor:
         bufs = self.static_cuda_buffers
-        bufs["last_tokens"][:B].copy_(input_ids, non_blocking=True)
-        bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)
+        if input_ids.data_ptr() != bufs["last_tokens"].data_ptr():
+            bufs["last_tokens"][:B].copy_(input_ids, non_blocking=True)
+        if previous_hidden_states.data_ptr() != bufs["previous_hidden_states"].data_ptr():
+            bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)
         padded = padding_size(B)
         key = (padded, S)
         g = self.cuda_graphs.get(key)

@@ -419,8 +419,11 @@ class ArcticLSTMSpeculator:
         """Copy the inputs (device or host tensors) into the static buffers, replay the graph of the
         padded batch and return a VIEW of the static output buffer (valid until the next call)."""
         bufs = self.static_cuda_buffers
-        bufs["last_tokens"][:B].copy_(input_ids, non_blocking=True)                        # :625
-        bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)   # :629
+        # inputs that already live in the static buffers (a caller that fills them in place) need no copy
+        if input_ids.data_ptr() != bufs["last_tokens"].data_ptr():
+            bufs["last_tokens"][:B].copy_(input_ids, non_blocking=True)                        # :625
+        if previous_hidden_states.data_ptr() != bufs["previous_hidden_states"].data_ptr():
+            bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)   # :629
         padded = padding_size(B)                                       # :631
         key = (padded, S)
         g = self.cuda_graphs.get(key)
