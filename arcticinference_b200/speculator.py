@@ -502,10 +502,18 @@ class ArcticProposer:
                 previous_hidden_states = previous_hidden_states.to(self.device, non_blocking=True)
             return m.generate_proposals(input_ids=input_ids, previous_hidden_states=previous_hidden_states,
                                         num_predict_tokens=S).cpu().numpy()
-        if ids.device.type == "cpu":
-            self._ids_pinned[:B].copy_(ids)
-            ids = self._ids_pinned[:B]
-        out_dev = m._replay(ids, previous_hidden_states, B, S)
+        if getattr(m, "tp_size", 1) == 1:
+            # the big copy (hidden states) goes first; both land straight in the graph's static buffers,
+            # so _replay finds its inputs in place and adds no staging copies
+            bufs = m.static_cuda_buffers
+            bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)
+            if ids.device.type == "cpu":
+                self._ids_pinned[:B].copy_(ids)
+                ids = self._ids_pinned[:B]
+            bufs["last_tokens"][:B].copy_(ids, non_blocking=True)
+            out_dev = m._replay(bufs["last_tokens"][:B], bufs["previous_hidden_states"][:B], B, S)
+        else:
+            out_dev = m.generate_proposals(ids.to(self.device), previous_hidden_states.to(self.device), S)
         out = self._out_pinned[:B * S].view(B, S)
         out.copy_(out_dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
