@@ -445,7 +445,9 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("gemm_bf16_tn_sm100<1>", {}).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            # dominant kernel = fused vocab-head GEMM + arg-max (EPI_ARGMAX, MT = 1, bf16)
+            traffic = (tj.get("gemm_tn_sm100<1, 1, 0>") or tj.get("gemm_bf16_tn_sm100<1>") or {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     step_kernel_ms = kern["rms_scale"] + S * (kern["gate_gemm"] + kern["cell"] + kern["head_argmax"])
@@ -469,7 +471,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "gemm_bf16_tn_sm100<EPI_ARGMAX> (vocab head + arg-max)",
+        "roofline": {"bound": "hbm", "kernel": "gemm_tn_sm100<EPI_ARGMAX, MT=1, bf16> (vocab head + arg-max)",
                      "achieved": head_gbs, "peak": peak, "unit": "GB/s", "frac": head_gbs / peak,
                      "traffic": traffic, "algorithmic_bytes": head_bytes,
                      "avg_launch_ms": kern["head_argmax"], "peak_source": peak_src,
