@@ -59,7 +59,8 @@ kv_write_bulk_kernel(const char* __restrict__ keys, const char* __restrict__ val
                      uint32_t row_bytes,        // n * e: one (token, layer) row
                      uint32_t chunks_per_row,   // row_bytes / VEC
                      int32_t cpr_shift,         // log2(chunks_per_row) or -1
-                     uint32_t total_chunks) {   // layers_in_this_launch * chunks_per_row
+                     uint32_t total_chunks,     // layers_in_this_launch * chunks_per_row
+                     uint32_t per_cta) {        // chunks per CTA: total split evenly over grid.y
   using V = typename VecT<VEC>::type;
   const int64_t token = blockIdx.x;
   const int64_t slot = __ldg(slot_mapping + token);
@@ -70,12 +71,13 @@ kv_write_bulk_kernel(const char* __restrict__ keys, const char* __restrict__ val
   const char* ksrc = keys + token * key_row_bytes;
   const char* vsrc = values + token * value_row_bytes;
 
-  const uint32_t q0 = blockIdx.y * (kKvThreads * kKvUnroll) + threadIdx.x;
+  const uint32_t q0 = blockIdx.y * per_cta + threadIdx.x;
+  const uint32_t q_end = min(total_chunks, (blockIdx.y + 1) * per_cta);
   V kreg[kKvUnroll], vreg[kKvUnroll];
 #pragma unroll
   for (int j = 0; j < kKvUnroll; ++j) {
     const uint32_t q = q0 + j * kKvThreads;
-    if (q < total_chunks) {
+    if (q < q_end) {
       kreg[j] = kv_ld<VEC>(ksrc + static_cast<int64_t>(q) * VEC);
       vreg[j] = kv_ld<VEC>(vsrc + static_cast<int64_t>(q) * VEC);
     }
@@ -83,7 +85,7 @@ kv_write_bulk_kernel(const char* __restrict__ keys, const char* __restrict__ val
 #pragma unroll
   for (int j = 0; j < kKvUnroll; ++j) {
     const uint32_t q = q0 + j * kKvThreads;
-    if (q < total_chunks) {
+    if (q < q_end) {
       const uint32_t layer = cpr_shift >= 0 ? (q >> cpr_shift) : (q / chunks_per_row);
       const uint32_t c = q - layer * chunks_per_row;
       const int64_t d = dst_row + static_cast<int64_t>(c) * VEC;
@@ -105,10 +107,13 @@ static int launch_kv(const char* keys, const char* values, int64_t krb, int64_t 
     while ((1u << shift) < cpr) ++shift;
   }
   const uint32_t total = cpr * static_cast<uint32_t>(layers);
-  const uint32_t per_cta = kKvThreads * kKvUnroll;
-  dim3 grid(static_cast<unsigned>(num_tokens), (total + per_cta - 1) / per_cta);
+  // split a token's chunks EVENLY over the CTAs of grid.y (18 KiB rows: 2 x 576 chunks, not 1024 + 128)
+  const uint32_t cap = kKvThreads * kKvUnroll;
+  const uint32_t gy = (total + cap - 1) / cap;
+  const uint32_t per_cta = (total + gy - 1) / gy;
+  dim3 grid(static_cast<unsigned>(num_tokens), gy);
   kv_write_bulk_kernel<VEC><<<grid, kKvThreads, 0, stream>>>(
-      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_bytes, cpr, shift, total);
+      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_bytes, cpr, shift, total, per_cta);
   AB200_CHECK_LAUNCH("kv_write_bulk_kernel");
   return AB200_OK;
 }
@@ -201,7 +206,7 @@ kv_write_bulk_fp8_kernel(const char* __restrict__ keys, const char* __restrict__
                          const __grid_constant__ KvFp8Table tbl,
                          const int64_t* __restrict__ slot_mapping, int64_t block_stride_bytes,
                          int32_t block_size, uint32_t row_elems, uint32_t chunks_per_row,
-                         int32_t cpr_shift, uint32_t total_chunks) {
+                         int32_t cpr_shift, uint32_t total_chunks, uint32_t per_cta) {
   constexpr int EPC = SRC == AB200_F32 ? 4 : 8;   // elements (= cache bytes) per 16-byte chunk
   const int64_t token = blockIdx.x;
   const int64_t slot = __ldg(slot_mapping + token);
@@ -211,12 +216,13 @@ kv_write_bulk_fp8_kernel(const char* __restrict__ keys, const char* __restrict__
   const int64_t dst_row = blk * block_stride_bytes + off * static_cast<int64_t>(row_elems);
   const char* ksrc = keys + token * key_row_bytes;
   const char* vsrc = values + token * value_row_bytes;
-  const uint32_t q0 = blockIdx.y * (kKvThreads * kKvUnroll) + threadIdx.x;
+  const uint32_t q0 = blockIdx.y * per_cta + threadIdx.x;
+  const uint32_t q_end = min(total_chunks, (blockIdx.y + 1) * per_cta);
   uint4 kreg[kKvUnroll], vreg[kKvUnroll];
 #pragma unroll
   for (int j = 0; j < kKvUnroll; ++j) {
     const uint32_t q = q0 + j * kKvThreads;
-    if (q < total_chunks) {
+    if (q < q_end) {
       kreg[j] = ld_stream_16(ksrc + static_cast<int64_t>(q) * 16);
       vreg[j] = ld_stream_16(vsrc + static_cast<int64_t>(q) * 16);
     }
@@ -224,7 +230,7 @@ kv_write_bulk_fp8_kernel(const char* __restrict__ keys, const char* __restrict__
 #pragma unroll
   for (int j = 0; j < kKvUnroll; ++j) {
     const uint32_t q = q0 + j * kKvThreads;
-    if (q < total_chunks) {
+    if (q < q_end) {
       const uint32_t layer = cpr_shift >= 0 ? (q >> cpr_shift) : (q / chunks_per_row);
       const uint32_t c = q - layer * chunks_per_row;
       const int64_t d = dst_row + static_cast<int64_t>(c) * EPC;
@@ -255,10 +261,12 @@ static int launch_kv_fp8(const char* keys, const char* values, int64_t krb, int6
     while ((1u << shift) < cpr) ++shift;
   }
   const uint32_t total = cpr * static_cast<uint32_t>(layers);
-  const uint32_t per_cta = kKvThreads * kKvUnroll;
-  dim3 grid(static_cast<unsigned>(num_tokens), (total + per_cta - 1) / per_cta);
+  const uint32_t cap = kKvThreads * kKvUnroll;
+  const uint32_t gy = (total + cap - 1) / cap;
+  const uint32_t per_cta = (total + gy - 1) / gy;
+  dim3 grid(static_cast<unsigned>(num_tokens), gy);
   kv_write_bulk_fp8_kernel<SRC, E5M2><<<grid, kKvThreads, 0, stream>>>(
-      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_elems, cpr, shift, total);
+      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_elems, cpr, shift, total, per_cta);
   AB200_CHECK_LAUNCH("kv_write_bulk_fp8_kernel");
   return AB200_OK;
 }
