@@ -65,8 +65,22 @@ kv_write_bulk_kernel(const char* __restrict__ keys, const char* __restrict__ val
   const int64_t token = blockIdx.x;
   const int64_t slot = __ldg(slot_mapping + token);
   if (slot < 0) return;  // padded token (kernels.cu:32-35)
-  const int64_t blk = slot / block_size;
-  const int64_t off = slot - blk * block_size;
+  // block / offset of the slot: a shift for power-of-two block sizes (block_size < 0 encodes
+  // -(log2 + 1)), else 32-bit or (for huge caches) 64-bit division - once per thread, but a
+  // 64-bit division costs as much as moving a whole chunk
+  int64_t blk, off;
+  if (block_size < 0) {
+    const int sh = -block_size - 1;
+    blk = slot >> sh;
+    off = slot & ((int64_t{1} << sh) - 1);
+  } else if (slot <= 0x7fffffffLL) {
+    const uint32_t s32 = static_cast<uint32_t>(slot), b32 = static_cast<uint32_t>(block_size);
+    blk = s32 / b32;
+    off = s32 - static_cast<uint32_t>(blk) * b32;
+  } else {
+    blk = slot / block_size;
+    off = slot - blk * block_size;
+  }
   const int64_t dst_row = blk * block_stride_bytes + off * static_cast<int64_t>(row_bytes);
   const char* ksrc = keys + token * key_row_bytes;
   const char* vsrc = values + token * value_row_bytes;
@@ -95,6 +109,16 @@ kv_write_bulk_kernel(const char* __restrict__ keys, const char* __restrict__ val
   }
 }
 
+// power-of-two block sizes travel as -(log2 + 1) so that the kernel shifts instead of dividing
+static int32_t encode_block_size(int32_t bs) {
+  if (bs > 0 && (bs & (bs - 1)) == 0) {
+    int sh = 0;
+    while ((1 << sh) < bs) ++sh;
+    return -(sh + 1);
+  }
+  return bs;
+}
+
 template <int VEC>
 static int launch_kv(const char* keys, const char* values, int64_t krb, int64_t vrb,
                      const KvPtrTable& tbl, int layers, const int64_t* slot_mapping,
@@ -113,7 +137,8 @@ static int launch_kv(const char* keys, const char* values, int64_t krb, int64_t 
   const uint32_t per_cta = (total + gy - 1) / gy;
   dim3 grid(static_cast<unsigned>(num_tokens), gy);
   kv_write_bulk_kernel<VEC><<<grid, kKvThreads, 0, stream>>>(
-      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_bytes, cpr, shift, total, per_cta);
+      keys, values, krb, vrb, tbl, slot_mapping, bsb, encode_block_size(block_size), row_bytes, cpr, shift, total,
+      per_cta);
   AB200_CHECK_LAUNCH("kv_write_bulk_kernel");
   return AB200_OK;
 }
@@ -211,8 +236,22 @@ kv_write_bulk_fp8_kernel(const char* __restrict__ keys, const char* __restrict__
   const int64_t token = blockIdx.x;
   const int64_t slot = __ldg(slot_mapping + token);
   if (slot < 0) return;
-  const int64_t blk = slot / block_size;
-  const int64_t off = slot - blk * block_size;
+  // block / offset of the slot: a shift for power-of-two block sizes (block_size < 0 encodes
+  // -(log2 + 1)), else 32-bit or (for huge caches) 64-bit division - once per thread, but a
+  // 64-bit division costs as much as moving a whole chunk
+  int64_t blk, off;
+  if (block_size < 0) {
+    const int sh = -block_size - 1;
+    blk = slot >> sh;
+    off = slot & ((int64_t{1} << sh) - 1);
+  } else if (slot <= 0x7fffffffLL) {
+    const uint32_t s32 = static_cast<uint32_t>(slot), b32 = static_cast<uint32_t>(block_size);
+    blk = s32 / b32;
+    off = s32 - static_cast<uint32_t>(blk) * b32;
+  } else {
+    blk = slot / block_size;
+    off = slot - blk * block_size;
+  }
   const int64_t dst_row = blk * block_stride_bytes + off * static_cast<int64_t>(row_elems);
   const char* ksrc = keys + token * key_row_bytes;
   const char* vsrc = values + token * value_row_bytes;
@@ -266,7 +305,8 @@ static int launch_kv_fp8(const char* keys, const char* values, int64_t krb, int6
   const uint32_t per_cta = (total + gy - 1) / gy;
   dim3 grid(static_cast<unsigned>(num_tokens), gy);
   kv_write_bulk_fp8_kernel<SRC, E5M2><<<grid, kKvThreads, 0, stream>>>(
-      keys, values, krb, vrb, tbl, slot_mapping, bsb, block_size, row_elems, cpr, shift, total, per_cta);
+      keys, values, krb, vrb, tbl, slot_mapping, bsb, encode_block_size(block_size), row_elems, cpr, shift, total,
+      per_cta);
   AB200_CHECK_LAUNCH("kv_write_bulk_fp8_kernel");
   return AB200_OK;
 }
