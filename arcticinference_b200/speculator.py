@@ -457,6 +457,7 @@ class ArcticProposer:
         # in one; no intermediate device tensors (the reference does .to(device) / .cpu(), :160-166)
         self._ids_pinned = torch.empty(n, dtype=torch.long).pin_memory()
         self._out_pinned = torch.empty(n * model.max_speculative_tokens, dtype=torch.long).pin_memory()
+        self._plans: Dict[Tuple[int, int], tuple] = {}
 
     def prepare_hidden_states(self, sample_hidden_states: torch.Tensor, sampled_token_ids: torch.Tensor,
                               num_draft_tokens: Optional[List[int]]) -> torch.Tensor:
@@ -503,17 +504,32 @@ class ArcticProposer:
             return m.generate_proposals(input_ids=input_ids, previous_hidden_states=previous_hidden_states,
                                         num_predict_tokens=S).cpu().numpy()
         if getattr(m, "tp_size", 1) == 1:
-            # the big copy (hidden states) goes first; both land straight in the graph's static buffers,
-            # so _replay finds its inputs in place and adds no staging copies
-            bufs = m.static_cuda_buffers
-            bufs["previous_hidden_states"][:B].copy_(previous_hidden_states, non_blocking=True)
+            # Steady state (graph captured): every tensor view is cached per (B, S), so a call is two H2D
+            # copies straight into the graph's static buffers (the big one first), one replay, one D2H
+            # and a stream sync - no Python-side slicing on the critical path.
+            plan = self._plans.get((B, S))
+            if plan is None:
+                bufs = m.static_cuda_buffers
+                m._replay(bufs["last_tokens"][:B], bufs["previous_hidden_states"][:B], B, S)   # capture if needed
+                padded = padding_size(B)
+                graph = m.cuda_graphs[(padded, S)]
+                out_dev = bufs["next_tokens"].view(-1)[:padded * S].view(padded, S)[:B]
+                out = self._out_pinned[:B * S].view(B, S)
+                plan = (bufs["previous_hidden_states"][:B], bufs["last_tokens"][:B], self._ids_pinned[:B],
+                        self._ids_pinned.numpy()[:B], graph, out_dev, out, out.numpy())
+                self._plans[(B, S)] = plan
+            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np = plan
+            hid_dev.copy_(previous_hidden_states, non_blocking=True)
             if ids.device.type == "cpu":
-                self._ids_pinned[:B].copy_(ids)
-                ids = self._ids_pinned[:B]
-            bufs["last_tokens"][:B].copy_(ids, non_blocking=True)
-            out_dev = m._replay(bufs["last_tokens"][:B], bufs["previous_hidden_states"][:B], B, S)
-        else:
-            out_dev = m.generate_proposals(ids.to(self.device), previous_hidden_states.to(self.device), S)
+                ids_np[:] = ids.numpy()
+                ids_dev.copy_(ids_pin, non_blocking=True)
+            else:
+                ids_dev.copy_(ids, non_blocking=True)
+            graph.replay()
+            out.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return out_np.copy()
+        out_dev = m.generate_proposals(ids.to(self.device), previous_hidden_states.to(self.device), S)
         out = self._out_pinned[:B * S].view(B, S)
         out.copy_(out_dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
