@@ -53,6 +53,7 @@ SIGNATURES = {
     "ab200_launch_count": (c_int64, []),
     "ab200_set_trace_buffer": (c_int32, [c_void_p, c_int32]),
     "ab200_debug_cell_generic": (c_int32, [c_int32]),
+    "ab200_debug_sigmoid_search": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_float, c_void_p]),
     "ab200_debug_unary_bf16": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int64, c_void_p]),
     "ab200_kv_write_bulk": (c_int32, [c_void_p, c_void_p, c_int64, c_int64,

@@ -226,12 +226,18 @@ sum_lstm_cell_kernel(const T* __restrict__ gates, int64_t ldg, const T* __restri
 // a third of the instructions - see bf16_exact.cuh for why each shortcut is exact.  Values that
 // live across the two row reductions are kept as packed bf16x2 (they ARE bf16 in eager mode).
 // ------------------------------------------------------------------------------------------
-// per-device copy of the GELU table of bf16_exact.cuh (1 KB, L2-resident)
-__device__ float g_gelu_lut[kGeluLutSize];
-__global__ void gelu_lut_init_kernel() { g_gelu_lut[threadIdx.x] = gelu_lut_entry(threadIdx.x); }
+// per-device copy of the GELU table of bf16_exact.cuh (8 KB, L2-resident)
+__device__ __align__(16) uint16_t g_gelu_tab[kGeluTabEntries];
+__global__ void gelu_lut_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kGeluTabEntries) g_gelu_tab[i] = gelu_tab_entry(i);
+}
 
 // FULL: D == 8 * ITEMS * blockDim.x (no ragged tail: bounds checks and zero-fills compile away)
-template <int ITEMS, int MAXT, int MINB, bool FULL, bool GUARD>
+// EXACT: bit-identical to eager PyTorch (guard-free fast sigmoid with a range test per 16-byte
+// vector, GELU by table); !EXACT: "faithful" - the same rounding points with the unguarded fast
+// sigmoid and polynomial GELU (differs from ATen by one bf16 ulp on the 0.13 % of GELU inputs <= -3).
+template <int ITEMS, int MAXT, int MINB, bool FULL, bool EXACT>
 __global__ void __launch_bounds__(MAXT, MINB)
 sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg,
                             const __nv_bfloat16* __restrict__ emb,
@@ -247,14 +253,15 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
                             uint8_t* __restrict__ state_q, float* __restrict__ state_scale) {
   using T = __nv_bfloat16;
   __shared__ float scratch[33], scratch2[32];
-  __shared__ float gelu_lut[kGeluLutSize];
+  __shared__ __align__(16) uint16_t gelu_tab[EXACT ? kGeluTabEntries : 8];
   const int64_t row = blockIdx.x;
   const int nvec = D / 8;
 
   if (threadIdx.x == 0) trace_stamp(trace, 0);
   pdl_launch_dependents();
-  if constexpr (GUARD) gelu_lut_fill(gelu_lut, g_gelu_lut);   // independent of the previous kernel
-  uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_lut));
+  // the table fill is independent of the previous kernel: it runs before the dependency wait
+  if constexpr (EXACT) gelu_tab_fill(gelu_tab, g_gelu_tab);
+  uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_tab));
   asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));   // opaque: keep it in a register, do not rematerialise
   pdl_wait();
   if (threadIdx.x == 0) {
@@ -271,7 +278,7 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
   uint4 lnw1[PRE ? ITEMS : 1], lnb1[PRE ? ITEMS : 1], lnw2[PRE ? ITEMS : 1], lnb2[PRE ? ITEMS : 1];
 
   uint32_t F[ITEMS][4], I[ITEMS][4], O[ITEMS][4], CC[ITEMS][4], C[ITEMS][4];
-  float ss = 0.f;
+  f2 ss2 = bcast2(0.f);   // sum of squares, even / odd elements (one FADD2 per pair)
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int vi = threadIdx.x + it * blockDim.x;
@@ -299,32 +306,34 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
       const uint32_t gfa[4] = {gf.x, gf.y, gf.z, gf.w}, gia[4] = {gi.x, gi.y, gi.z, gi.w};
       const uint32_t goa[4] = {go.x, go.y, go.z, go.w}, gca[4] = {gc.x, gc.y, gc.z, gc.w};
       const uint32_t zea[4] = {ze.x, ze.y, ze.z, ze.w}, cpa[4] = {cp.x, cp.y, cp.z, cp.w};
+      uint32_t af[4], ai[4], ao[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const f2 zz = unpack2(zea[p]), al = bcast2(alpha);
         // torch.add(states, z.repeat(1,1,4), alpha): one rounding of fma(alpha, z, s)
         const f2 sf = fma2(al, zz, unpack2(gfa[p])), si = fma2(al, zz, unpack2(gia[p]));
         const f2 so = fma2(al, zz, unpack2(goa[p])), sc = fma2(al, zz, unpack2(gca[p]));
-        const uint32_t af = pack_rn(sf.a, sf.b), ai = pack_rn(si.a, si.b), ao = pack_rn(so.a, so.b);
+        af[p] = pack_rn(sf.a, sf.b);
+        ai[p] = pack_rn(si.a, si.b);
+        ao[p] = pack_rn(so.a, so.b);
         CC[it][p] = pack_rn(sc.a, sc.b);
-        sigmoid6_bf16_exact<GUARD>(af, ai, ao, F[it][p], I[it][p], O[it][p]);
         C[it][p] = cpa[p];
-        const uint32_t sq = mul2(CC[it][p], CC[it][p]);
-        ss += bf_lo(sq);
-        ss += bf_hi(sq);
+        ss2 = add2f(ss2, unpack2(mul2(CC[it][p], CC[it][p])));
+        if constexpr (!EXACT) sigmoid6_bf16_exact<false>(af[p], ai[p], ao[p], F[it][p], I[it][p], O[it][p]);
       }
+      if constexpr (EXACT) sigmoid24_bf16_exact<true>(af, ai, ao, F[it], I[it], O[it]);
     } else if constexpr (!FULL) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) F[it][p] = I[it][p] = O[it][p] = CC[it][p] = C[it][p] = 0u;
     }
   }
   // cell_ln (RMS, affine) -> GELU -> * input gate ; c = c_prev * f + candidate
-  ss = block_sum_1sync(ss, scratch);   // also orders gelu_lut_fill before the first table read
+  float ss = block_sum_1sync(ss2.a + ss2.b, scratch);   // also orders the table fill before its first read
   {
     const float mean = ST<T>::round(ss * inv_d);
     const float inv = ST<T>::round(rsqrtf(ST<T>::round(mean + eps)));
     const uint32_t inv2 = pack_rn(inv, inv);
-    ss = 0.f;
+    ss2 = bcast2(0.f);
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
       const int vi = threadIdx.x + it * blockDim.x;
@@ -338,25 +347,24 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
           b = *reinterpret_cast<const uint4*>(bc + vi * 8);
         }
         const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
+        uint32_t y[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          uint32_t y = mul2(CC[it][p], inv2);
-          y = mul2(wa[p], y);
-          y = add2(y, ba[p]);
-          y = gelu2_bf16_exact<GUARD>(y, lut_s);
-          y = mul2(y, I[it][p]);
-          uint32_t cn = mul2(C[it][p], F[it][p]);
-          cn = add2(cn, y);
+          y[p] = add2(mul2(wa[p], mul2(CC[it][p], inv2)), ba[p]);
+          if constexpr (!EXACT) y[p] = gelu2_bf16_exact<false>(y[p], lut_s);
+        }
+        if constexpr (EXACT) gelu8_bf16_table(y, lut_s);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const uint32_t cn = add2(mul2(C[it][p], F[it][p]), mul2(y[p], I[it][p]));
           C[it][p] = cn;
-          const uint32_t sq = mul2(cn, cn);
-          ss += bf_lo(sq);
-          ss += bf_hi(sq);
+          ss2 = add2f(ss2, unpack2(mul2(cn, cn)));
         }
       }
     }
   }
   // state_ln (RMS, affine) -> GELU -> * output gate
-  ss = block_sum_1sync(ss, scratch2);
+  ss = block_sum_1sync(ss2.a + ss2.b, scratch2);
   {
     const float mean = ST<T>::round(ss * inv_d);
     const float inv = ST<T>::round(rsqrtf(ST<T>::round(mean + eps)));
@@ -374,14 +382,15 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
           b = *reinterpret_cast<const uint4*>(bs + vi * 8);
         }
         const uint32_t wa[4] = {w.x, w.y, w.z, w.w}, ba[4] = {b.x, b.y, b.z, b.w};
+        uint32_t y[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          uint32_t y = mul2(C[it][p], inv2);
-          y = mul2(wa[p], y);
-          y = add2(y, ba[p]);
-          y = gelu2_bf16_exact<GUARD>(y, lut_s);
-          F[it][p] = mul2(y, O[it][p]);   // the new state (F is dead: reuse its registers)
+          y[p] = add2(mul2(wa[p], mul2(C[it][p], inv2)), ba[p]);
+          if constexpr (!EXACT) y[p] = gelu2_bf16_exact<false>(y[p], lut_s);
         }
+        if constexpr (EXACT) gelu8_bf16_table(y, lut_s);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) F[it][p] = mul2(y[p], O[it][p]);   // the new state (F is dead: reuse its registers)
         *reinterpret_cast<uint4*>(state_out + row * D + vi * 8) =
             make_uint4(F[it][0], F[it][1], F[it][2], F[it][3]);
         *reinterpret_cast<uint4*>(cell_out + row * D + vi * 8) =
@@ -425,18 +434,28 @@ __global__ void unary_bf16_kernel(int op, const uint16_t* __restrict__ in, uint1
                                   uint16_t* __restrict__ exact, float* __restrict__ fast32,
                                   float* __restrict__ exact32, int64_t n) {
   __shared__ float gelu_lut[kGeluLutSize];
+  __shared__ __align__(16) uint16_t gelu_tab[kGeluTabEntries];
 #pragma unroll 1
   for (int i = threadIdx.x; i < kGeluLutSize; i += blockDim.x) gelu_lut[i] = gelu_lut_entry(i);
+#pragma unroll 1
+  for (int i = threadIdx.x; i < kGeluTabEntries; i += blockDim.x) gelu_tab[i] = gelu_tab_entry(i);
   uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_lut));
   asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));
+  uint32_t tab_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_tab));
+  asm volatile("mov.u32 %0, %0;" : "+r"(tab_s));
   __syncthreads();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float x = __uint_as_float(static_cast<uint32_t>(in[i]) << 16);
-    const uint32_t x2 = static_cast<uint32_t>(in[i]) * 0x10001u;
+    // ops 2 / 3: table GELU on the pair (in[i], in[n-1-i]); 2 reports the low half, 3 the high half
+    const uint16_t xin = op == 3 ? in[n - 1 - i] : in[i];
+    const float x = __uint_as_float(static_cast<uint32_t>(xin) << 16);
+    const uint32_t x2 = op >= 2 ? static_cast<uint32_t>(in[i]) | (static_cast<uint32_t>(in[n - 1 - i]) << 16)
+                                : static_cast<uint32_t>(in[i]) * 0x10001u;
     uint32_t f, f_i, f_o;
     if (op == 0) sigmoid6_bf16_exact<true>(x2, x2, x2, f, f_i, f_o);
-    else f = gelu2_bf16_exact<true>(x2, lut_s);
+    else if (op == 1) f = gelu2_bf16_exact<true>(x2, lut_s);
+    else f = gelu2_bf16_table(x2, tab_s);
+    if (op == 3) f >>= 16;
     const float e = op == 0 ? sigmoid_aten(x) : gelu_erf_aten(x);
     fast[i] = static_cast<uint16_t>(f & 0xFFFFu);
     exact[i] = static_cast<uint16_t>(pack_rn(e, 0.f) & 0xFFFFu);
@@ -448,9 +467,62 @@ __global__ void unary_bf16_kernel(int op, const uint16_t* __restrict__ in, uint1
   }
 }
 
+// Search hook for the guard-free sigmoid: candidate c = (c1, k, addend) evaluates
+// rcp(fma(ex2(x * c1), k, addend)) on all 65 536 bf16 inputs x >= lo_bound and counts the inputs whose
+// bf16 rounding differs from ATen's formula (tools/sigmoid_search.py).  One block per candidate.
+__global__ void sigmoid_search_kernel(const float* __restrict__ cand, uint32_t* __restrict__ mismatches,
+                                      uint32_t* __restrict__ first_bad, float lo_bound) {
+  const float c1 = cand[3 * blockIdx.x], k = cand[3 * blockIdx.x + 1], addend = cand[3 * blockIdx.x + 2];
+  uint32_t count = 0u, bad = 0xffffffffu;
+  for (uint32_t bits = threadIdx.x; bits < 65536u; bits += blockDim.x) {
+    const float x = __uint_as_float(bits << 16);
+    if (!(x >= lo_bound)) continue;
+    const float s = rcp_approx(__fmaf_rn(ex2_approx(__fmul_rn(x, c1)), k, addend));
+    const uint32_t fast = pack_rn(s, 0.f) & 0xffffu, exact = pack_rn(sigmoid_aten(x), 0.f) & 0xffffu;
+    if (fast != exact) {
+      ++count;
+      bad = min(bad, bits);
+    }
+  }
+  if (count) {
+    atomicAdd(mismatches + blockIdx.x, count);
+    atomicMin(first_bad + blockIdx.x, bad);
+  }
+}
+
+// Same search for the polynomial GELU on y > lo_bound: candidate = (the last two coefficients and the
+// -1 term); arithmetic as in half_erfc2 / gelu2_bf16_exact.
+__global__ void gelu_search_kernel(const float* __restrict__ cand, uint32_t* __restrict__ mismatches,
+                                   uint32_t* __restrict__ first_bad, float lo_bound) {
+  const float c5 = cand[3 * blockIdx.x], c6 = cand[3 * blockIdx.x + 1], cm1 = cand[3 * blockIdx.x + 2];
+  uint32_t count = 0u, bad = 0xffffffffu;
+  for (uint32_t bits = threadIdx.x; bits < 65536u; bits += blockDim.x) {
+    const float y = __uint_as_float(bits << 16);
+    if (!(y > lo_bound)) continue;
+    const float u = fminf(fabsf(y), 5.6568542494923806f);
+    float q = 4.4679095481e-06f;
+    q = __fmaf_rn(q, u, -1.4861870113e-05f);
+    q = __fmaf_rn(q, u, -5.6600669632e-04f);
+    q = __fmaf_rn(q, u, 7.6454123482e-03f);
+    q = __fmaf_rn(q, u, -5.2912395447e-02f);
+    q = __fmaf_rn(q, u, c5);
+    q = __fmaf_rn(q, u, c6);
+    const float h = ex2_approx(__fmaf_rn(q, u, cm1));
+    const float g = __fmul_rn(y, (bits & 0x8000u) ? h : __fsub_rn(1.0f, h));
+    const uint32_t fast = pack_rn(g, 0.f) & 0xffffu, exact = pack_rn(gelu_erf_aten(y), 0.f) & 0xffffu;
+    if (fast != exact) {
+      ++count;
+      bad = min(bad, bits);
+    }
+  }
+  if (count) {
+    atomicAdd(mismatches + blockIdx.x, count);
+    atomicMin(first_bad + blockIdx.x, bad);
+  }
+}
+
 // debug switch (ab200_debug_cell_generic): 1 = run the generic kernel also for bf16 + emulation
 static int g_cell_generic = 0;
-
 // block size / items-per-thread for a row of `nvec` 16-byte vectors
 static bool row_launch_shape(int64_t nvec, int* threads, int* items) {
   for (int it : {1, 2, 4}) {
@@ -491,7 +563,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
                        const void* bc, const void* ws, const void* bs, void* state_out,
                        void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
                        uint64_t* clear_packed, uint32_t* clear_counter, void* state_q,
-                       float* state_scale, bool guard, cudaStream_t s) {
+                       float* state_scale, bool exact, cudaStream_t s) {
   int threads, items;
   AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
                 "sum_lstm_cell: D %lld too large", (long long)D);
@@ -522,7 +594,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       int dev = 0;
       AB200_CUDA_OK(cudaGetDevice(&dev));
       if (dev < 0 || dev >= 64 || !lut_ready[dev]) {
-        gelu_lut_init_kernel<<<1, kGeluLutSize, 0, s>>>();
+        gelu_lut_init_kernel<<<kGeluTabEntries / 256, 256, 0, s>>>();
         AB200_CHECK_LAUNCH("gelu_lut_init_kernel");
         lc.cfg.numAttrs = 0;
         // under stream capture the fill only runs when the graph is replayed: keep filling until an
@@ -540,7 +612,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       vocab, alpha, eps, inv_d, a_clear, a_cnt, a_trace, a_sq, state_scale
 #define AB200_FAST_LAUNCH2(IT, MAXT, MINB, FULLV)                                                 \
   do {                                                                                           \
-    if (guard)                                                                                   \
+    if (exact)                                                                                   \
       AB200_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, sum_lstm_cell_bf16x2_kernel<IT, MAXT, MINB, FULLV, true>, \
                                        AB200_FAST_ARGS));                                        \
     else                                                                                         \
@@ -658,10 +730,25 @@ extern "C" int32_t ab200_debug_cell_generic(int32_t on) {
   return prev;
 }
 
+extern "C" int32_t ab200_debug_sigmoid_search(const float* candidates, int32_t n_candidates,
+                                              uint32_t* mismatches, uint32_t* first_bad,
+                                              float lo_bound, void* stream) {
+  AB200_REQUIRE(candidates && mismatches && first_bad && n_candidates != 0, AB200_E_INVALID,
+                "debug_sigmoid_search: bad arguments");
+  if (n_candidates < 0)   // negative count: the GELU search
+    gelu_search_kernel<<<-n_candidates, 256, 0, static_cast<cudaStream_t>(stream)>>>(candidates, mismatches,
+                                                                                     first_bad, lo_bound);
+  else
+    sigmoid_search_kernel<<<n_candidates, 256, 0, static_cast<cudaStream_t>(stream)>>>(candidates, mismatches,
+                                                                                       first_bad, lo_bound);
+  AB200_CHECK_LAUNCH("sigmoid_search_kernel");
+  return AB200_OK;
+}
+
 extern "C" int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16_t* out_fast,
                                           uint16_t* out_exact, float* out_fast32,
                                           float* out_exact32, int64_t n, void* stream) {
-  AB200_REQUIRE((op == 0 || op == 1) && in && out_fast && out_exact && n > 0, AB200_E_INVALID,
+  AB200_REQUIRE(op >= 0 && op <= 3 && in && out_fast && out_exact && n > 0, AB200_E_INVALID,
                 "debug_unary_bf16: bad arguments");
   unary_bf16_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(op, in, out_fast, out_exact,
                                                                          out_fast32, out_exact32, n);

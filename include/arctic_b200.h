@@ -244,8 +244,15 @@ AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
  *   The two must agree bit for bit (tests/test_cell_gpu.py).
  * ab200_debug_unary_bf16: op 0 = sigmoid, 1 = erf-GELU on n bf16 bit patterns; out_fast is the
  *   cell kernel's shortcut, out_exact ATen's formula (csrc/bf16_exact.cuh), both rounded to bf16;
- *   out_fast32 / out_exact32: the unguarded approximation and ATen's value in fp32. */
+ *   out_fast32 / out_exact32: the unguarded approximation and ATen's value in fp32.
+ * ab200_debug_sigmoid_search: for each candidate (c1, k, addend) [n_candidates x 3 floats, device]
+ *   counts the bf16 inputs x >= lo_bound where RN(rcp(fma(ex2(x*c1), k, addend))) differs from ATen's
+ *   sigmoid (mismatches[c], zero-initialised by the caller) and the lowest such input (first_bad[c],
+ *   initialised to 0xffffffff).  Used once, offline, to pick constants that need no rounding guard. */
 AB200_API int32_t ab200_debug_cell_generic(int32_t on);
+AB200_API int32_t ab200_debug_sigmoid_search(const float* candidates, int32_t n_candidates,
+                                             uint32_t* mismatches, uint32_t* first_bad, float lo_bound,
+                                             void* stream);
 AB200_API int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16_t* out_fast,
                                          uint16_t* out_exact, float* out_fast32 /*optional*/,
                                          float* out_exact32 /*optional*/, int64_t n, void* stream);

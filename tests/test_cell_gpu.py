@@ -58,6 +58,25 @@ def test_unary_shortcuts_exact_on_all_65536_inputs(capi, op, name):
                       f"{[(hex(bits[i].item() & 0xFFFF), x[i].item()) for i in bad[:8]]}")
 
 
+@pytest.mark.parametrize("op", [2, 3])
+def test_gelu_table_exact_on_all_65536_inputs(capi, op):
+    """The 8 KB GELU table path (default exact mode): pairs (x[i], x[65535-i]) so that both halves of
+    a bf16x2 take different routes (in-window / out-of-window / NaN); op 2 checks the low half, op 3
+    the high half."""
+    bits, x = all_bf16()
+    fast = torch.empty_like(bits)
+    exact = torch.empty_like(bits)
+    capi.check(capi.lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
+                                                 None, None, 65536, st()))
+    torch.cuda.synchronize()
+    xin = x if op == 2 else x.flip(0)
+    ref = torch.nn.functional.gelu(xin).view(torch.int16)
+    ok = nan_equal_bits(fast, ref)
+    bad = (~ok).nonzero().flatten()
+    assert ok.all(), (f"table GELU differs from torch on {bad.numel()} inputs, e.g. "
+                      f"{[(hex(xin.view(torch.int16)[i].item() & 0xFFFF), xin[i].item()) for i in bad[:8]]}")
+
+
 def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
     B, D4 = gates.shape
     D = D4 // 4

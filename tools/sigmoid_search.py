@@ -1,0 +1,58 @@
+"""Offline search for guard-free sigmoid constants (run once on a B200).
+
+fast(x) = rcp.approx(fma(ex2.approx(x * c1), k, addend)) with (c1, k, addend) a few fp32 ulps around
+(-log2 e, 1, 1).  For every candidate the kernel counts, over ALL bf16 inputs x >= lo_bound, how many
+round to a different bf16 than ATen's 1/(1+expf(-x)).  A candidate with zero mismatches needs no
+near-tie guard in the cell kernel: exactness is then a finite, exhaustively checked statement
+(tests/test_cell_gpu.py re-checks it on every run)."""
+import itertools
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from arcticinference_b200 import _capi
+
+
+def ulp_steps(v: float, lo: int, hi: int):
+    b = np.float32(v).view(np.int32)
+    return [float(np.int32(b + d).view(np.float32)) for d in range(lo, hi + 1)]
+
+
+dev = torch.device("cuda:0")
+c1s = ulp_steps(-1.4426950408889634, -8, 8)
+ks = ulp_steps(1.0, -8, 8)
+adds = ulp_steps(1.0, -4, 4)
+cands = list(itertools.product(c1s, ks, adds))
+ct = torch.tensor(cands, dtype=torch.float32, device=dev).contiguous()
+st = torch.cuda.current_stream().cuda_stream
+base = cands.index((c1s[8], 1.0, 1.0))
+for lo_bound in (-16.0, -24.0, -40.0, -87.0, -3.0e38):
+    mism = torch.zeros(len(cands), dtype=torch.int32, device=dev)
+    first = torch.full((len(cands),), -1, dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().ab200_debug_sigmoid_search(ct.data_ptr(), len(cands), mism.data_ptr(), first.data_ptr(),
+                                                       lo_bound, st), "search")
+    torch.cuda.synchronize()
+    m = mism.cpu().numpy()
+    order = np.argsort(m, kind="stable")
+    print(f"lo_bound {lo_bound}: baseline (-log2e, 1, 1) mismatches = {m[base]}; zero-mismatch candidates = {(m == 0).sum()} "
+          f"of {len(cands)}; histogram of counts: {np.bincount(np.minimum(m, 10)).tolist()}")
+    for i in order[:6]:
+        c = cands[i]
+        print(f"   mism={m[i]} c1={np.float32(c[0]).view(np.uint32):#x} ({c[0]!r}) k={np.float32(c[1]).view(np.uint32):#x} "
+              f"({c[1]!r}) add={np.float32(c[2]).view(np.uint32):#x} ({c[2]!r}) first_bad={int(first[i]) & 0xffff:#06x}")
+    # robustness: candidates whose 26 neighbours in the (c1, k, addend) lattice are also zero
+    grid = m.reshape(len(c1s), len(ks), len(adds))
+    best = None
+    for a in range(1, len(c1s) - 1):
+        for b in range(1, len(ks) - 1):
+            for c in range(1, len(adds) - 1):
+                tot = int(grid[a - 1:a + 2, b - 1:b + 2, c - 1:c + 2].sum())
+                if grid[a, b, c] == 0 and (best is None or tot < best[0]):
+                    best = (tot, a, b, c)
+    if best:
+        tot, a, b, c = best
+        print(f"   most robust zero: c1={np.float32(c1s[a]).view(np.uint32):#x} k={np.float32(ks[b]).view(np.uint32):#x} "
+              f"add={np.float32(adds[c]).view(np.uint32):#x} (mismatches summed over its 27-neighbourhood: {tot})")
