@@ -2,7 +2,7 @@
 // of the instruction count (used by the fused LSTM cell kernel, lstm_cell.cu).
 //
 // PyTorch eager computes every bf16 elementwise op in fp32 and rounds its output to bf16
-// (SURVEY.md 7-H1).  Three facts make that cheap to reproduce exactly:
+// (SURVEY.md 7-H1).  Two facts make that cheap to reproduce exactly:
 //
 //  1. For bf16 operands, fp32 add / mul followed by a bf16 rounding equals the correctly rounded
 //     bf16 result (double rounding is innocuous when the wide format has >= 2p+2 = 18 significand

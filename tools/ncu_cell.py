@@ -16,9 +16,10 @@ cprev = torch.randn(B, D, device=dev).to(torch.bfloat16)
 state = torch.empty(B, D, device=dev, dtype=torch.bfloat16); cell = torch.empty_like(state)
 x = torch.randn(B, D, device=dev).to(torch.bfloat16); y = torch.empty_like(x)
 for _ in range(3):
-    _capi.check(lib.ab200_sum_lstm_cell(gates.data_ptr(), 4 * D, emb.data_ptr(), toks.data_ptr(), None, cprev.data_ptr(),
-                                        ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr(),
-                                        state.data_ptr(), cell.data_ptr(), B, D, V, 23.07, 1e-6, 2, 1, None, None, None, None, st))
+    for mode in (1, 2):   # exact, faithful: capture with  -k regex:sum_lstm_cell -s 2 -c 2
+        _capi.check(lib.ab200_sum_lstm_cell(gates.data_ptr(), 4 * D, emb.data_ptr(), toks.data_ptr(), None, cprev.data_ptr(),
+                                            ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr(),
+                                            state.data_ptr(), cell.data_ptr(), B, D, V, 23.07, 1e-6, 2, mode, None, None, None, None, st))
     _capi.check(lib.ab200_rms_scale(x.data_ptr(), y.data_ptr(), B, D, D, D, 1e-6, 0.70710678, 2, 1, st))
 torch.cuda.synchronize()
 print("ok", state.float().abs().mean().item())
