@@ -62,6 +62,8 @@ unsigned long long* next_trace_slot();
 
 // rows of a batch that share one pass over the weights in the tcgen05 GEMMs (gemm_sm100.cu)
 int gemm_rows_per_pass();
+// 1 (default): the GEMM kernels signal their dependents only after their own dependency wait
+int gemm_late_trigger();
 
 struct LaunchCfg {
   cudaLaunchConfig_t cfg;

@@ -814,6 +814,10 @@ static int env_int(const char* name, int dflt);
 // rows the MT = 4 variant is left with 64-column tiles and becomes bound by the L2 -> SM ingest
 // of the activation tiles (measured 568 us vs 2 x 222 us for the 8B head); AB200_ROWS_PER_PASS=512
 // re-enables it.
+int ab200::gemm_late_trigger() {
+  static const int v = env_int("AB200_LATE_TRIGGER", 1);
+  return v;
+}
 int ab200::gemm_rows_per_pass() {
   static const int v = [] {
     const int e = env_int("AB200_ROWS_PER_PASS", 256);
@@ -871,7 +875,7 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.num_k_blocks = static_cast<int32_t>((K + k_elems - 1) / k_elems);
   p.stages = stages;
   p.l2_prefetch_kb = pdl_enabled() ? env_int("AB200_L2_PREFETCH_KB", 0) : 0;
-  p.late_trigger = env_int("AB200_LATE_TRIGGER", 1);
+  p.late_trigger = gemm_late_trigger();
   p.pre_stages = env_int("AB200_PRE_STAGES", stages);
   if (p.pre_stages > stages) p.pre_stages = stages;
   if (p.pre_stages < 0) p.pre_stages = 0;
@@ -943,7 +947,7 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
   p.stages = stages;
   p.l2_prefetch_kb = 0;
-  p.late_trigger = env_int("AB200_LATE_TRIGGER", 1);
+  p.late_trigger = gemm_late_trigger();
   p.pre_stages = env_int("AB200_PRE_STAGES", stages);
   if (p.pre_stages > stages) p.pre_stages = stages;
   if (p.pre_stages < 0) p.pre_stages = 0;

@@ -250,7 +250,7 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
                             int64_t vocab, float alpha, float eps, float inv_d,
                             unsigned long long* __restrict__ clear_packed,
                             unsigned int* __restrict__ clear_counter, unsigned long long* trace,
-                            uint8_t* __restrict__ state_q, float* __restrict__ state_scale) {
+                            uint8_t* __restrict__ state_q, float* __restrict__ state_scale, int early) {
   using T = __nv_bfloat16;
   __shared__ float scratch[33], scratch2[32];
   __shared__ __align__(16) uint16_t gelu_tab[EXACT ? kGeluTabEntries : 8];
@@ -263,46 +263,89 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
   if constexpr (EXACT) gelu_tab_fill(gelu_tab, g_gelu_tab);
   uint32_t lut_s = static_cast<uint32_t>(__cvta_generic_to_shared(gelu_tab));
   asm volatile("mov.u32 %0, %0;" : "+r"(lut_s));   // opaque: keep it in a register, do not rematerialise
+  // Latency variant (batches of at most ~one CTA per SM): the LayerNorm vectors are fetched up front
+  // instead of after each row reduction, so that their L2 latency is off the critical path.
+  constexpr bool PRE = MAXT == 512 && MINB == 1;
+  const T* g = gates + row * ldg;
+  int64_t tok = 0;
+  uint4 lnw1[PRE ? ITEMS : 1], lnb1[PRE ? ITEMS : 1], lnw2[PRE ? ITEMS : 1], lnb2[PRE ? ITEMS : 1];
+  uint4 zeP[PRE ? ITEMS : 1], cpP[PRE ? ITEMS : 1];
+  // Everything but the gate pre-activations: token -> embedding row, previous cell state, LayerNorm
+  // vectors.  With `early` (set by the draft loop, where the kernel before this one is the gate GEMM
+  // and all of these were complete before THAT kernel started) it runs before the dependency wait,
+  // so that only the L2-hot gate rows are still to be fetched once the GEMM has finished.
+  auto fetch_side_inputs = [&]() {
+    tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
+    if constexpr (PRE) {
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int vi = threadIdx.x + it * blockDim.x;
+        if (FULL || vi < nvec) {
+          cpP[it] = cell_prev ? ld_ordered_16(cell_prev + row * D + vi * 8) : make_uint4(0u, 0u, 0u, 0u);
+          lnw1[it] = ld_ordered_16(wc + vi * 8);
+          lnb1[it] = ld_ordered_16(bc + vi * 8);
+          lnw2[it] = ld_ordered_16(ws + vi * 8);
+          lnb2[it] = ld_ordered_16(bs + vi * 8);
+        }
+      }
+      int64_t tk = tok;
+      if (static_cast<uint64_t>(tk) >= static_cast<uint64_t>(vocab)) tk = tk < 0 ? 0 : vocab - 1;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int vi = threadIdx.x + it * blockDim.x;
+        if (FULL || vi < nvec) zeP[it] = ld_stream_16(emb + tk * static_cast<int64_t>(D) + vi * 8);
+      }
+    }
+  };
+  const bool early_side = PRE && early;
+  if (early_side) fetch_side_inputs();
   pdl_wait();
   if (threadIdx.x == 0) {
     trace_stamp(trace, 1);
     if (clear_packed) clear_packed[row] = 0ull;
     if (clear_counter && row == 0) *clear_counter = 0u;
   }
-  // Latency variant (batches of at most ~one CTA per SM): the LayerNorm vectors are fetched up front
-  // instead of after each row reduction, so that their L2 latency is off the critical path.
-  constexpr bool PRE = MAXT == 512 && MINB == 1;
-  int64_t tok = packed ? static_cast<int64_t>(unpack_idx(packed[row])) : tokens[row];
-
-  const T* g = gates + row * ldg;
-  uint4 lnw1[PRE ? ITEMS : 1], lnb1[PRE ? ITEMS : 1], lnw2[PRE ? ITEMS : 1], lnb2[PRE ? ITEMS : 1];
 
   uint32_t F[ITEMS][4], I[ITEMS][4], O[ITEMS][4], CC[ITEMS][4], C[ITEMS][4];
   f2 ss2 = bcast2(0.f);   // sum of squares, even / odd elements (one FADD2 per pair)
+  uint4 gfv[PRE ? ITEMS : 1], giv[PRE ? ITEMS : 1], gov[PRE ? ITEMS : 1], gcv[PRE ? ITEMS : 1];
+  if constexpr (PRE) {
+    // gate rows first (they are what the wait was for), then - unless already in flight - the rest
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (FULL || vi < nvec) {
+        gfv[it] = ld_stream_16(g + 0 * D + vi * 8);
+        giv[it] = ld_stream_16(g + 1 * D + vi * 8);
+        gov[it] = ld_stream_16(g + 2 * D + vi * 8);
+        gcv[it] = ld_stream_16(g + 3 * D + vi * 8);
+      }
+    }
+    if (!early_side) fetch_side_inputs();
+  } else {
+    fetch_side_inputs();
+  }
 #pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int vi = threadIdx.x + it * blockDim.x;
     if (FULL || vi < nvec) {
-      const uint4 gf = ld_stream_16(g + 0 * D + vi * 8);
-      const uint4 gi = ld_stream_16(g + 1 * D + vi * 8);
-      const uint4 go = ld_stream_16(g + 2 * D + vi * 8);
-      const uint4 gc = ld_stream_16(g + 3 * D + vi * 8);
-      uint4 cp = make_uint4(0u, 0u, 0u, 0u);
+      uint4 gf, gi, go, gc, cp, ze;
       if constexpr (PRE) {
-        if (cell_prev) cp = ld_ordered_16(cell_prev + row * D + vi * 8);
-        lnw1[it] = ld_ordered_16(wc + vi * 8);
-        lnb1[it] = ld_ordered_16(bc + vi * 8);
-        lnw2[it] = ld_ordered_16(ws + vi * 8);
-        lnb2[it] = ld_ordered_16(bs + vi * 8);
+        gf = gfv[it], gi = giv[it], go = gov[it], gc = gcv[it], cp = cpP[it], ze = zeP[it];
       } else {
+        gf = ld_stream_16(g + 0 * D + vi * 8);
+        gi = ld_stream_16(g + 1 * D + vi * 8);
+        go = ld_stream_16(g + 2 * D + vi * 8);
+        gc = ld_stream_16(g + 3 * D + vi * 8);
+        cp = make_uint4(0u, 0u, 0u, 0u);
         if (cell_prev) cp = *reinterpret_cast<const uint4*>(cell_prev + row * D + vi * 8);
+        // everything that does not depend on the token is in flight before the token is consumed
+        // (the embedding row is the only load behind the token's L2 round trip)
+        asm volatile("" : "+l"(tok));
+        int64_t tk = tok;
+        if (static_cast<uint64_t>(tk) >= static_cast<uint64_t>(vocab)) tk = tk < 0 ? 0 : vocab - 1;
+        ze = ld_stream_16(emb + tk * static_cast<int64_t>(D) + vi * 8);
       }
-      // everything that does not depend on the token is in flight before the token is consumed
-      // (the embedding row is the only load behind the token's L2 round trip)
-      asm volatile("" : "+l"(tok));
-      int64_t tk = tok;
-      if (static_cast<uint64_t>(tk) >= static_cast<uint64_t>(vocab)) tk = tk < 0 ? 0 : vocab - 1;
-      const uint4 ze = ld_stream_16(emb + tk * static_cast<int64_t>(D) + vi * 8);
       const uint32_t gfa[4] = {gf.x, gf.y, gf.z, gf.w}, gia[4] = {gi.x, gi.y, gi.z, gi.w};
       const uint32_t goa[4] = {go.x, go.y, go.z, go.w}, gca[4] = {gc.x, gc.y, gc.z, gc.w};
       const uint32_t zea[4] = {ze.x, ze.y, ze.z, ze.w}, cpa[4] = {cp.x, cp.y, cp.z, cp.w};
@@ -563,7 +606,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
                        const void* bc, const void* ws, const void* bs, void* state_out,
                        void* cell_out, int64_t B, int64_t D, int64_t vocab, float alpha, float eps,
                        uint64_t* clear_packed, uint32_t* clear_counter, void* state_q,
-                       float* state_scale, bool exact, cudaStream_t s) {
+                       float* state_scale, bool exact, int early, cudaStream_t s) {
   int threads, items;
   AB200_REQUIRE(row_launch_shape(D / Vec16<T>::N, &threads, &items), AB200_E_INVALID,
                 "sum_lstm_cell: D %lld too large", (long long)D);
@@ -609,7 +652,7 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       const bool full = D == 8LL * items * threads;
 #define AB200_FAST_ARGS                                                                          \
   a_gates, ldg, a_emb, tokens, a_packed, a_cprev, a_wc, a_bc, a_ws, a_bs, a_state, a_cell, a_D, \
-      vocab, alpha, eps, inv_d, a_clear, a_cnt, a_trace, a_sq, state_scale
+      vocab, alpha, eps, inv_d, a_clear, a_cnt, a_trace, a_sq, state_scale, early
 #define AB200_FAST_LAUNCH2(IT, MAXT, MINB, FULLV)                                                 \
   do {                                                                                           \
     if (exact)                                                                                   \
@@ -707,11 +750,14 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
                     (!cell_prev || aligned(cell_prev, 16)),
                 AB200_E_INVALID, "sum_lstm_cell: pointers must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int early = (emulate_eager_rounding & AB200_CELL_SIDE_INPUTS_READY) ? 1 : 0;
+  emulate_eager_rounding &= ~AB200_CELL_SIDE_INPUTS_READY;
   const bool emu = emulate_eager_rounding != 0;
 #define AB200_ARGS                                                                               \
   gates, gates_row_stride, emb_table, tokens, packed_argmax, cell_prev, cell_ln_weight,          \
       cell_ln_bias, state_ln_weight, state_ln_bias, state_out, cell_out, B, D, vocab, alpha, eps, \
-      clear_packed, clear_counter, state_q_out, state_scale_out, emulate_eager_rounding != 2, s
+      clear_packed, clear_counter, state_q_out, state_scale_out, emulate_eager_rounding != 2,    \
+      early, s
   switch (dtype) {
     case AB200_F32: return launch_cell<float, false>(AB200_ARGS);
     case AB200_BF16:

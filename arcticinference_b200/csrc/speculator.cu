@@ -186,7 +186,10 @@ extern "C" int32_t ab200_lstm_propose(const ab200_lstm_speculator* sp, const int
                              step == 0 ? nullptr : packed + static_cast<size_t>(step - 1) * B,
                              cell_prev, sp->cell_ln_w, sp->cell_ln_b, sp->state_ln_w, sp->state_ln_b,
                              state, cell, B, D, sp->vocab, sp->alpha, sp->eps, sp->dtype,
-                             sp->emulate_eager_rounding,
+                             // the gate GEMM just launched signals its dependents only after it has
+                             // itself waited for everything before it: tokens, cell state and
+                             // weights are complete by the time this kernel can start
+                             sp->emulate_eager_rounding | (gemm_late_trigger() ? AB200_CELL_SIDE_INPUTS_READY : 0),
                              fused_tokens ? packed + static_cast<size_t>(step) * B : nullptr,
                              fused_tokens ? counters + step : nullptr, state_q, state_scale, stream);
     if (rc != AB200_OK) return rc;

@@ -138,7 +138,13 @@ AB200_API int32_t ab200_rms_scale(const void* x, void* y, int64_t rows, int64_t 
  *   sigmoid / erf-GELU round exactly as ATen's CUDA kernels do (bit-identical states);
  *   2 (bf16) = the same rounding points with unguarded fast sigmoid / GELU ("faithful": about
  *   0.1 % of the elements differ from mode 1 by one bf16 ulp) for the bandwidth-bound regime.
+ *   OR-ing AB200_CELL_SIDE_INPUTS_READY into it promises that everything except `gates` (tokens /
+ *   packed_argmax, cell_prev, the LayerNorm vectors, the embedding table) was complete before the
+ *   kernel that PRECEDES this launch in the stream started; the kernel may then fetch them before
+ *   its programmatic-dependent-launch wait (the draft loop sets it: the predecessor there is the
+ *   gate GEMM).  Without the flag nothing is read before the wait.
  * D must be a multiple of 8 (16-byte vectors). */
+#define AB200_CELL_SIDE_INPUTS_READY 0x100
 AB200_API int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stride,
                             const void* emb_table, const int64_t* tokens,
                             const uint64_t* packed_argmax,
