@@ -1,7 +1,9 @@
 """GPU: the bf16x2 fused-cell kernel (production: bf16 + eager-rounding emulation) is bit-identical
 to (i) PyTorch's own CUDA bf16 sigmoid / erf-GELU on ALL 65 536 bf16 inputs, (ii) the generic
 (instruction-heavy, ATen-formula) cell kernel on random and adversarial rows, (iii) the op-for-op
-oracle.  See arcticinference_b200/csrc/bf16_exact.cuh for the argument why the shortcuts are exact."""
+oracle.  See arcticinference_b200/csrc/bf16_exact.cuh for the argument why the shortcuts are exact: the
+fast sigmoid and the GELU table are exact BY EXHAUSTION over the 65 536 bf16 inputs, and the first two tests
+here are that exhaustion, re-run on whatever device the suite runs on."""
 import pytest
 import torch
 
