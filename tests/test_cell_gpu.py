@@ -107,7 +107,8 @@ def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
     (16, 256, 6.0, True),        # saturated gates: |x| up to ~25
     (5, 40, 1.0, True),          # D not a multiple of 64: ragged last warp
     (3, 20000, 1.5, True),       # ITEMS = 4 path
-    (2048, 1024, 1.3, True),
+    (2048, 1024, 1.3, True), (2304, 4096, 1.3, True), (2100, 4096, 1.3, False), (2051, 2880, 1.0, True),
+    (4099, 512, 2.0, True),      # >= 4096 rows: 16 elements per thread
 ])
 def test_bf16x2_kernel_bit_identical_to_generic_kernel(capi, B, D, gate_std, with_prev):
     torch.manual_seed(B * 131 + D)
