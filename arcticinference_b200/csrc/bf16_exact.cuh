@@ -103,13 +103,6 @@ AB200_SETP2(setp2_gt, "gt")
 AB200_SETP2(setp2_lt, "lt")
 #undef AB200_SETP2
 
-// true iff the low 16 bits of v are within K of the bf16 rounding tie 0x8000:
-// ((bits + K - 0x8000) mod 2^16) <= 2K, evaluated in the top half of a 32-bit word (IMAD + ISETP)
-template <uint32_t K>
-__device__ __forceinline__ bool near_bf16_tie(float v) {
-  return __float_as_uint(v) * 0x10000u + ((K - 0x8000u) << 16) <= ((2u * K) << 16);
-}
-
 // ATen CUDA functors, verbatim arithmetic (the slow, exact paths)
 static __device__ __noinline__ float sigmoid_aten(float x) { return 1.0f / (1.0f + expf(-x)); }
 static __device__ __noinline__ float gelu_erf_aten(float x) {
@@ -189,28 +182,6 @@ __device__ __forceinline__ void gelu_lut_fill(float* lut, const float* __restric
 // GELU(y) = y * Phi(y).  With u = |y|: erfc(u/sqrt2)/2 = 2^(u*Q(u) - 1), Q = degree-6 fit of
 // log2(erfc(u/sqrt2))/u on [0, 4*sqrt2] (relative error <= 14 fp32 ulps for u <= 2, absolute
 // <= 2e-8 above); Phi(y) = that for y < 0 (no cancellation) and 1 - that for y >= 0.
-__device__ __forceinline__ float gelu_fast(float y, bool negative) {
-  const float u = fminf(fabsf(y), 5.6568542494923806f);
-  float q = 4.4679095481e-06f;
-  q = fmaf(q, u, -1.4861870113e-05f);
-  q = fmaf(q, u, -5.6600669632e-04f);
-  q = fmaf(q, u, 7.6454123482e-03f);
-  q = fmaf(q, u, -5.2912395447e-02f);
-  q = fmaf(q, u, -4.5906913280e-01f);
-  q = fmaf(q, u, -1.1511206627e+00f);
-  const float h = ex2_approx(fmaf(u, q, -1.0f));
-  return y * (negative ? h : 1.0f - h);
-}
-// y in (-8, -2]: ATen's 1 + erff(..) cancels and its fp32 noise decides the bf16 result -> the
-// table (256 inputs).  `lut_s` = 32-bit shared-window address of the table (one LDS, no generic
-// address arithmetic).
-__device__ __forceinline__ float gelu_fast_lut(float y, bool negative, uint32_t lut_s) {
-  float g = gelu_fast(y, negative);
-  const uint32_t off = (__float_as_uint(y) >> 14) - (0xC000u << 2);   // byte offset into the table
-  if (off < static_cast<uint32_t>(kGeluLutSize) * 4u)
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(lut_s + off));
-  return g;
-}
 // erfc(|y|/sqrt2)/2 for a pair, the polynomial in packed fp32
 __device__ __forceinline__ f2 half_erfc2(f2 y) {
   const f2 u = f2{fminf(fabsf(y.a), 5.6568542494923806f), fminf(fabsf(y.b), 5.6568542494923806f)};
