@@ -366,7 +366,8 @@ def bench_kv_write(dev, iters: int, peak_gbs: float):
     return out
 
 
-def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096, V: int = 128256, iters: int = 10):
+def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096, V: int = 128256, iters: int = 10,
+                          ln_scale: float = 1.0):
     """The fused cell in its bandwidth-bound regime (at the BASELINE batch sizes it is
     launch-latency bound): `rows` x D bf16, algorithmic bytes = rows*D*2*8 + 4*D*2 + 8*rows."""
     import torch
@@ -375,7 +376,7 @@ def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096
     st = torch.cuda.current_stream(dev).cuda_stream
     g = torch.Generator(device=dev).manual_seed(0)
     emb = (torch.randn(V, D, device=dev, generator=g) * 0.02).to(torch.bfloat16)
-    ln = [(torch.randn(D, device=dev, generator=g) * 0.1 + (1 if i % 2 == 0 else 0)).to(torch.bfloat16) for i in range(4)]
+    ln = [((torch.randn(D, device=dev, generator=g) * 0.1 + (1 if i % 2 == 0 else 0)) * ln_scale).to(torch.bfloat16) for i in range(4)]
     gates = (torch.randn(rows, 4 * D, device=dev, generator=g) * 1.3).to(torch.bfloat16)
     toks = torch.randint(0, V, (rows,), device=dev, generator=g)
     cprev = torch.randn(rows, D, device=dev, generator=g).to(torch.bfloat16)
