@@ -79,6 +79,23 @@ def test_gelu_table_exact_on_all_65536_inputs(capi, op):
                       f"{[(hex(xin.view(torch.int16)[i].item() & 0xFFFF), xin[i].item()) for i in bad[:8]]}")
 
 
+@pytest.mark.parametrize("kind,lo_bound,consts", [
+    ("sigmoid", -87.0, (-1.4426950408889634, 1.0, 1.0)),                   # rcp(fma(ex2(x*c1), k, addend))
+    ("gelu", -3.0, (-4.5906913280e-01, -1.1511206627e+00, -1.0)),           # last two coefficients, -1 term
+])
+def test_fast_paths_need_no_rounding_guard(capi, kind, lo_bound, consts):
+    """The claim the kernels rely on (bf16_exact.cuh): with the production constants, the fast sigmoid rounds to
+    the same bf16 as ATen's formula for EVERY input x >= -87, and the polynomial GELU for every y > -3."""
+    cand = torch.tensor([consts], dtype=torch.float32, device=DEV)
+    mism = torch.zeros(1, dtype=torch.int32, device=DEV)
+    first = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+    n = 1 if kind == "sigmoid" else -1
+    capi.check(capi.lib().ab200_debug_sigmoid_search(cand.data_ptr(), n, mism.data_ptr(), first.data_ptr(),
+                                                     lo_bound, st()))
+    torch.cuda.synchronize()
+    assert mism.item() == 0, f"{kind}: {mism.item()} inputs misround, first {hex(first.item() & 0xFFFF)}"
+
+
 def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
     B, D4 = gates.shape
     D = D4 // 4
