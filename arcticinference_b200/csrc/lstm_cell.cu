@@ -647,7 +647,6 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
         if (dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone) lut_ready[dev] = true;
       }
       // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
-      // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
       const float inv_d = 1.0f / static_cast<float>(D);
       const bool full = D == 8LL * items * threads;
 #define AB200_FAST_ARGS                                                                          \
