@@ -844,11 +844,14 @@ template <int EPI, int MT, int KIND>
 static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
                             int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one flag per device ordinal (one process may drive several)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  AB200_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100<EPI, MT, KIND>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int sms = sm_count();
   const int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
@@ -910,11 +913,13 @@ template <int EPI>
 static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
                                  int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out, int64_t ldo,
                                  const ArgmaxExtra& ax, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  AB200_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100_2cta<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int pairs = sm_count() / 2;
   // tile width: multiple of 32 (each CTA holds half of it), balanced over the CTA pairs
