@@ -195,6 +195,7 @@ struct GemmParams {
   unsigned long long* trace;   // optional timeline slot (profiling)
   const float* x_scales;       // KIND_FP8: per-row activation scales [m_rows]
   const float* w_scale;        // KIND_FP8: per-tensor weight scale [1]
+  uint32_t a_slot;             // bytes of a stage reserved for the activation tile(s)
 };
 
 // K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -214,7 +215,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
                    const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   constexpr int kAccSlot = kMaxBlockN / MT;   // TMEM columns per (buffer, m-tile); block_n <= kAccSlot
-  constexpr uint32_t kASlot = MT * kABytes;
+  // UMMA M = 64 (<= 64 batch rows) needs an 8 KiB activation slot instead of 16: more stages, i.e.
+  // more weight bytes in flight per SM
+  const uint32_t kASlot = MT == 1 ? p.a_slot : MT * kABytes;
   constexpr int kKElems = KIND == KIND_BF16 ? 64 : 128;   // elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -857,7 +860,13 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   const int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
   const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
   const int box_m = MT == 1 ? static_cast<int>((m_rows + 7) / 8 * 8) : kTileM;
-  const uint32_t stage_bytes = MT * kABytes + bn * 128;
+  // weight bytes in flight per SM = stages x tile: with a 7-stage ring the 8B gate GEMM was bound by
+  // (bytes in flight) / (HBM latency) = 56-61 GB/s per SM, not by HBM - the activation slot is
+  // therefore sized to the rows the batch really has
+  // (the MMA reads all M rows of the slot, valid or not: M = 64 -> 8 KiB, M = 128 -> 16 KiB)
+  const bool m64 = MT == 1 && m_rows <= 64 && env_int("AB200_UMMA_M64", 1);
+  const uint32_t a_slot = m64 ? 64u * 128u : MT * kABytes;
+  const uint32_t stage_bytes = a_slot + bn * 128;
   int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
@@ -887,11 +896,12 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   // kind::f8f6f4: 0 = e4m3), K-major A/B, N>>3 [17,23), M>>4 [24,29)
   const uint32_t fmt = KIND == KIND_BF16 ? 1u : 0u;
   // <= 64 rows: UMMA M = 64 halves the tensor-pipe work (and power) of this HBM-bound kernel
-  p.m64 = (MT == 1 && m_rows <= 64 && env_int("AB200_UMMA_M64", 1)) ? 1 : 0;
+  p.m64 = m64 ? 1 : 0;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
             (static_cast<uint32_t>((p.m64 ? 64 : kTileM) >> 4) << 24);
   p.x_scales = ax.x_scales;
   p.w_scale = ax.w_scale;
+  p.a_slot = a_slot;
   p.out = out;
   p.ldo = ldo;
   p.packed = ax.packed;
