@@ -457,6 +457,10 @@ struct GatherTable {
   int32_t count;
 };
 
+constexpr int kGatherUnroll = 4;
+
+// One CTA = one output row x one slab of 256 * kGatherUnroll 16-byte chunks of the concatenated rows
+// of all tensors; a thread has up to four independent 16-byte loads in flight before its first store.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restrict__ indices,
                    int64_t num_src_rows) {
@@ -465,21 +469,35 @@ gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restr
   if (src_row < 0) src_row += num_src_rows;                       // torch index_select accepts negatives
   if (src_row < 0 || src_row >= num_src_rows) return;             // (host validates; never read outside)
   const uint32_t total = t.chunk_begin[t.count];
-  for (uint32_t q = blockIdx.y * blockDim.x + threadIdx.x; q < total; q += gridDim.y * blockDim.x) {
-    int k = 0;
+  for (uint32_t base = blockIdx.y * (256u * kGatherUnroll) + threadIdx.x; base < total;
+       base += gridDim.y * (256u * kGatherUnroll)) {
+    uint4 reg[kGatherUnroll];
+    char* dptr[kGatherUnroll];
 #pragma unroll
-    for (int i = 1; i < kGatherMaxTensors; ++i)
-      if (i < t.count && q >= t.chunk_begin[i]) k = i;
-    const uint32_t c = q - t.chunk_begin[k];
-    const char* s = t.src[k] + src_row * t.src_stride[k] + static_cast<int64_t>(c) * 16;
-    char* d = t.dst[k] + out_row * t.dst_stride[k] + static_cast<int64_t>(c) * 16;
-    const uint32_t left = t.row_bytes[k] - c * 16;
-    if (t.vec16[k] && left >= 16) {
-      st_stream_16(d, ld_stream_16(s));
-    } else {
-      const uint32_t nb = left < 16 ? left : 16;
-      for (uint32_t b = 0; b < nb; ++b) d[b] = s[b];
+    for (int j = 0; j < kGatherUnroll; ++j) {
+      const uint32_t q = base + j * 256u;
+      dptr[j] = nullptr;
+      if (q < total) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < kGatherMaxTensors; ++i)
+          if (i < t.count && q >= t.chunk_begin[i]) k = i;
+        const uint32_t c = q - t.chunk_begin[k];
+        const char* s = t.src[k] + src_row * t.src_stride[k] + static_cast<int64_t>(c) * 16;
+        char* d = t.dst[k] + out_row * t.dst_stride[k] + static_cast<int64_t>(c) * 16;
+        const uint32_t left = t.row_bytes[k] - c * 16;
+        if (t.vec16[k] && left >= 16) {
+          reg[j] = ld_stream_16(s);
+          dptr[j] = d;
+        } else {   // unaligned tensor or ragged row end: bytes
+          const uint32_t nb = left < 16 ? left : 16;
+          for (uint32_t b = 0; b < nb; ++b) d[b] = s[b];
+        }
+      }
     }
+#pragma unroll
+    for (int j = 0; j < kGatherUnroll; ++j)
+      if (dptr[j] != nullptr) st_stream_16(dptr[j], reg[j]);
   }
 }
 }  // namespace ab200
@@ -517,7 +535,8 @@ extern "C" int32_t ab200_gather_rows(const void* const* src_ptrs, void* const* d
   t.chunk_begin[kGatherMaxTensors] = acc;
   for (int i = num_tensors; i <= kGatherMaxTensors; ++i) t.chunk_begin[i] = acc;
   t.count = num_tensors;
-  unsigned gy = (acc + 255) / 256;
+  const unsigned slab = 256u * kGatherUnroll;
+  unsigned gy = (acc + slab - 1) / slab;
   if (gy > 64) gy = 64;
   dim3 grid(static_cast<unsigned>(num_indices), gy);
   gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, indices, num_src_rows);

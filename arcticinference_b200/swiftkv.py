@@ -35,7 +35,8 @@ def gather_rows(tensors: Sequence[torch.Tensor], indices: torch.Tensor,
         raise NotImplementedError("gather_rows: CUDA tensors only (no CPU fallback)")
     if indices.dtype != torch.int64 or indices.dim() != 1:
         raise RuntimeError("gather_rows: indices must be a 1-D int64 tensor")
-    indices = indices.to(dev).contiguous()
+    if indices.device != dev or not indices.is_contiguous():
+        indices = indices.to(dev).contiguous()
     m = indices.numel()
     rows0 = tensors[0].shape[0]
     results: List[torch.Tensor] = []
@@ -66,12 +67,17 @@ def gather_rows(tensors: Sequence[torch.Tensor], indices: torch.Tensor,
     if not keep:
         return results
     k = len(keep)
-    P, I64 = ctypes.c_void_p * k, ctypes.c_int64 * k
-    with torch.cuda.device(dev):
-        rc = lib.ab200_gather_rows(P(*[srcs[i] for i in keep]), P(*[dsts[i] for i in keep]),
-                                   I64(*[ss[i] for i in keep]), I64(*[ds[i] for i in keep]),
-                                   I64(*[rb[i] for i in keep]), k, indices.data_ptr(), m, rows0,
-                                   _capi.current_stream_ptr(dev))
+    # one host buffer for the five per-tensor arrays of the C ABI (pointers are 8 bytes, like the int64s)
+    flat = (ctypes.c_int64 * (5 * k))(*[srcs[i] for i in keep], *[dsts[i] for i in keep], *[ss[i] for i in keep],
+                                      *[ds[i] for i in keep], *[rb[i] for i in keep])
+    base = ctypes.addressof(flat)
+    if torch.cuda.current_device() == dev.index:
+        rc = lib.ab200_gather_rows(base, base + 8 * k, base + 16 * k, base + 24 * k, base + 32 * k, k,
+                                   indices.data_ptr(), m, rows0, _capi.current_stream_ptr(dev))
+    else:
+        with torch.cuda.device(dev):
+            rc = lib.ab200_gather_rows(base, base + 8 * k, base + 16 * k, base + 24 * k, base + 32 * k, k,
+                                       indices.data_ptr(), m, rows0, _capi.current_stream_ptr(dev))
     _capi.check(rc, "ab200_gather_rows")
     return results
 

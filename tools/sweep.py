@@ -187,6 +187,29 @@ def sweep_kv(rows):
         del kv, kc, vc, keys, vals
 
 
+def sweep_gather(rows):
+    """SwiftKV select compaction (llama_swiftkv.py:669-685): five index_selects in one launch."""
+    from arcticinference_b200 import swiftkv
+    T, Hd, Ln = 8192, 4096, 16 * 1024
+    g = torch.Generator(device=dev).manual_seed(0)
+    hid = torch.randn(T, Hd, device=dev, generator=g).to(torch.bfloat16)
+    res = torch.randn(T, Hd, device=dev, generator=g).to(torch.bfloat16)
+    pos = torch.arange(T, device=dev)
+    k = torch.randn(T, Ln, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(T, Ln, device=dev, generator=g).to(torch.bfloat16)
+    for m in (64, 256, 2048, 4096):
+        idx = torch.randperm(T, device=dev, generator=g)[:m].sort().values
+        tensors = [hid, res, pos, k, v]
+        outs = [torch.empty((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in tensors]
+        t_ours = timeit(lambda: swiftkv.gather_rows(tensors, idx, outs))
+        t_aten = timeit(lambda: [torch.index_select(t, 0, idx, out=o) for t, o in zip(tensors, outs)])
+        alg = 2 * m * sum(t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size() for t in tensors) + 8 * m
+        rows.append({"kernel": "gather_rows", "T": T, "selected": m, "us": t_ours, "gbs": alg / t_ours / 1e3,
+                     "hbm_frac": alg / t_ours / 1e3 / HBM, "aten_5x_index_select_us": t_aten})
+        print(f"[gather T={T}] selected={m:5d} {t_ours:8.1f} us {alg / t_ours / 1e3:6.0f} GB/s ({alg / t_ours / 1e3 / HBM:.2f} hbm) | "
+              f"5 x torch.index_select {t_aten:8.1f} us", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
@@ -206,6 +229,8 @@ def main():
         sweep_cell(rows, 4096, 128256, [1, 64, 256, 1024, 4096, 16384])
     if not only or "kv" in only:
         sweep_kv(rows)
+    if not only or "gather" in only:
+        sweep_gather(rows)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump({"peaks": PEAKS, "rows": rows}, open(a.out, "w"), indent=1)
     print("wrote", a.out)
