@@ -493,8 +493,26 @@ class ArcticProposer:
         assert num_predict_tokens > 0, \
             f"num_predict_tokens must be greater than 0, got {num_predict_tokens}."
         m = self.model
+        S = num_predict_tokens
+        # Steady state first: the hidden-state H2D copy is the long pole of the call (0.5 MB over PCIe), so it is
+        # enqueued before ANY other host work; everything below overlaps with it.
+        plan = self._plans.get((previous_hidden_states.shape[0], S)) if previous_hidden_states.dim() == 2 else None
+        if plan is not None and previous_hidden_states.shape[1] == m.input_hidden_dim:
+            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np = plan
+            hid_dev.copy_(previous_hidden_states, non_blocking=True)
+            ids = torch.as_tensor(context_token_ids)
+            if ids.dim() == 1 and ids.shape[0] == hid_dev.shape[0]:
+                if ids.device.type == "cpu":
+                    ids_np[:] = ids.numpy()
+                    ids_dev.copy_(ids_pin, non_blocking=True)
+                else:
+                    ids_dev.copy_(ids, non_blocking=True)
+                graph.replay()
+                out.copy_(out_dev, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return out_np.copy()
         ids = torch.as_tensor(context_token_ids)
-        B, S = ids.shape[0], num_predict_tokens
+        B = ids.shape[0]
         fast = (m.cuda_graph_mode and 0 < B <= m.cuda_graph_max_batch_size and S <= m.max_speculative_tokens
                 and ids.dim() == 1 and previous_hidden_states.shape == (B, m.input_hidden_dim))
         if not fast:
