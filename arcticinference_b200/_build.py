@@ -1,5 +1,10 @@
 """In-tree build of libarctic_b200.so: plain nvcc, sm_100a only, no torch headers (seconds, not
-minutes).  The .so is git-ignored but travels to the GPU box with the gpurun snapshot."""
+minutes).  The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+
+Two flavours from the same sources:
+  libarctic_b200.so      the product: compiled-in launch parameters, no ab200_debug_* symbol
+  libarctic_b200_dbg.so  -DAB200_DEBUG: adds the exhaustive-search / comparator hooks and
+                         ab200_debug_set_tunable; loaded by tests/ and tools/ only (_capi.debug_lib)."""
 from __future__ import annotations
 
 import os
@@ -10,6 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libarctic_b200.so")
+LIB_DEBUG = os.path.join(HERE, "libarctic_b200_dbg.so")
 SOURCES = ["kv_write.cu", "lstm_cell.cu", "mlp_cell.cu", "gemm_sm100.cu", "quant_fp8.cu", "speculator.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -24,26 +30,28 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def needs_build(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "arctic_b200.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    lib = LIB_DEBUG if debug else LIB
+    if not force and not needs_build(lib):
+        return lib
     nvcc = nvcc_path()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", "dbg" if debug else "rel")
     os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + (["-DAB200_DEBUG"] if debug else [])
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -56,12 +64,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    tmp = LIB + ".tmp"
+    tmp = lib + ".tmp"
     subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fPIC",
                            "-gencode", "arch=compute_100a,code=sm_100a"])
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build(force, verbose, debug=False), build(force, verbose, debug=True)
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(*build_all(force="--force" in sys.argv, verbose="-v" in sys.argv), sep="\n")

@@ -9,6 +9,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p, POIN
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libarctic_b200.so")
+DEBUG_LIB_PATH = os.path.join(HERE, "libarctic_b200_dbg.so")
 
 AB200_F32, AB200_F16, AB200_BF16 = 0, 1, 2
 AB200_KV_AUTO, AB200_KV_FP8_E4M3, AB200_KV_FP8_E5M2 = 0, 1, 2
@@ -30,7 +31,7 @@ class LstmSpeculatorDesc(ctypes.Structure):
     ]
 
 
-AB200_MLP_MAX_STAGES = 8
+AB200_MLP_MAX_STAGES = 16
 _PtrArr = c_void_p * AB200_MLP_MAX_STAGES
 
 
@@ -51,11 +52,8 @@ SIGNATURES = {
     "ab200_last_error": (c_char_p, []),
     "ab200_abi_version": (c_int32, []),
     "ab200_launch_count": (c_int64, []),
+    "ab200_init": (c_int32, [c_void_p]),
     "ab200_set_trace_buffer": (c_int32, [c_void_p, c_int32]),
-    "ab200_debug_cell_generic": (c_int32, [c_int32]),
-    "ab200_debug_sigmoid_search": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_float, c_void_p]),
-    "ab200_debug_unary_bf16": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_int64, c_void_p]),
     "ab200_kv_write_bulk": (c_int32, [c_void_p, c_void_p, c_int64, c_int64,
                                       POINTER(c_void_p), POINTER(c_void_p),
                                       POINTER(c_void_p), POINTER(c_void_p), c_int32,
@@ -99,35 +97,65 @@ SIGNATURES = {
     "ab200_sum_mlp_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int64, c_int64, c_int64, c_float, c_float, c_int32,
                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ab200_debug_mlp_generic": (c_int32, [c_int32]),
     "ab200_mlp_workspace_bytes": (c_size_t, [POINTER(MlpSpeculatorDesc), c_int64, c_int32]),
     "ab200_mlp_propose": (c_int32, [POINTER(MlpSpeculatorDesc), c_void_p, c_void_p, c_int64, c_int64,
                                     c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
+# exported by the debug flavour only (libarctic_b200_dbg.so, -DAB200_DEBUG): tests/ and tools/
+DEBUG_SIGNATURES = {
+    "ab200_debug_cell_generic": (c_int32, [c_int32]),
+    "ab200_debug_sigmoid_search": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_float, c_void_p]),
+    "ab200_debug_unary_bf16": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int64, c_void_p]),
+    "ab200_debug_mlp_generic": (c_int32, [c_int32]),
+    "ab200_debug_set_tunable": (c_int32, [c_char_p, c_int32]),
+}
+
 _lib = None
+_debug_lib = None
+
+
+def _load(path: str, signatures) -> ctypes.CDLL:
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing - build it with `python -m arcticinference_b200._build` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    handle = ctypes.CDLL(path)
+    for name, (res, args) in signatures.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    return handle
 
 
 def lib() -> ctypes.CDLL:
     """Load (once) and return the native library. Raises RuntimeError if it is not built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing - build it with `python -m arcticinference_b200._build` "
-                "(there is no CPU or PyTorch fallback for this path)")
-        handle = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = handle
+        _lib = _load(LIB_PATH, SIGNATURES)
     return _lib
 
 
-def check(rc: int, what: str = "") -> None:
+def debug_lib() -> ctypes.CDLL:
+    """The debug flavour (same kernels + ab200_debug_* hooks and settable launch tunables).  Test and
+    tool infrastructure only: nothing in the product package calls this."""
+    global _debug_lib
+    if _debug_lib is None:
+        _debug_lib = _load(DEBUG_LIB_PATH, {**SIGNATURES, **DEBUG_SIGNATURES})
+    return _debug_lib
+
+
+def init_device(device=None) -> None:
+    """ab200_init on `device` (function attributes, constant tables): call before capturing graphs."""
+    import torch
+    with torch.cuda.device(device):
+        check(lib().ab200_init(current_stream_ptr(device)), "ab200_init")
+
+
+def check(rc: int, what: str = "", handle=None) -> None:
     if rc != 0:
-        msg = lib().ab200_last_error().decode("utf-8", "replace")
+        msg = (handle or lib()).ab200_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libarctic_b200 {what} failed (code {rc}): {msg}")
 
 

@@ -7,8 +7,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/arctic_b200.h"
 
@@ -49,21 +51,99 @@ void count_launch(int n = 1);
     ::ab200::count_launch();                                                      \
   } while (0)
 
+// Launch-path tunables.  The release library uses the compiled-in defaults below (nothing on a launch
+// path reads the environment); the debug flavour (-DAB200_DEBUG, libarctic_b200_dbg.so, loaded by
+// tests/ and tools/ only) can change them through ab200_debug_set_tunable for parameter sweeps.
+struct Tune {
+  int pdl = 1;             // programmatic dependent launch between the kernels of a draft step
+  int umma_m64 = 1;        // <= 64 batch rows: UMMA M = 64 (8 KiB activation slot -> more stages)
+  int gemm_2cta = 1;       // 129..256 rows: CTA-pair kernel (tcgen05 cta_group::2)
+  int rows_per_pass = 256; // batch rows that share one pass over the weights (128 / 256 / 512)
+  int late_trigger = 1;    // GEMMs signal their dependents only after their own dependency wait
+  int pre_stages = -1;     // smem stages filled with W before the dependency wait (-1 = all)
+  int l2_prefetch_kb = 0;  // extra W k-blocks prefetched into L2 before the dependency wait
+  int gate_block_n = 0;    // debug: force the tile width of the store-epilogue GEMM (0 = heuristic)
+  int head_block_n = 0;    // debug: force the tile width of the arg-max GEMM
+  int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)
+  int early_producer = 1;  // TMA producer starts streaming W before TMEM allocation completes
+  int dyn_tiles = 0;       // debug: reserved
+};
+#ifdef AB200_DEBUG
+Tune& tune_mut();
+inline const Tune& tune() { return tune_mut(); }
+#else
+inline const Tune& tune() {
+  static constexpr Tune kTune{};
+  return kTune;
+}
+#endif
+
 // Programmatic dependent launch (PDL): kernels of one draft step are chained so that kernel N+1's
 // prologue (barrier init, TMEM allocation, weight prefetch) overlaps kernel N's tail.  Every
 // kernel calls pdl_launch_dependents() early and pdl_wait() before touching anything the previous
-// kernel produced; both are no-ops for launches without the attribute.  AB200_PDL=0 disables it.
-bool pdl_enabled();
+// kernel produced; both are no-ops for launches without the attribute.
+inline bool pdl_enabled() { return tune().pdl != 0; }
 
 // Optional device-side timeline (ab200_set_trace_buffer): every traced launch owns 4 u64 slots
 // {min CTA entry, min time after the PDL wait, max CTA exit, unused} of %globaltimer nanoseconds.
-// next_trace_slot() returns nullptr when tracing is off.
+// next_trace_slot() returns nullptr when tracing is off.  The trace state is per host thread.
 unsigned long long* next_trace_slot();
 
 // rows of a batch that share one pass over the weights in the tcgen05 GEMMs (gemm_sm100.cu)
-int gemm_rows_per_pass();
+inline int gemm_rows_per_pass() {
+  const int e = tune().rows_per_pass;
+  return e >= 512 ? 512 : (e >= 256 ? 256 : 128);
+}
 // 1 (default): the GEMM kernels signal their dependents only after their own dependency wait
-int gemm_late_trigger();
+inline int gemm_late_trigger() { return tune().late_trigger; }
+
+// ---- per-device one-time state (thread-safe) --------------------------------------------------
+constexpr int kMaxDevices = 64;
+// SM count of the CURRENT device (cached per device ordinal)
+int device_sm_count();
+// One-time per-device work that must have COMPLETED before any later launch on any stream may rely
+// on it (constant-table fills).  `fill(stream)` enqueues the work; device_once runs it once per
+// device under a mutex and synchronises the stream, so other threads / streams can never observe a
+// partly filled table.  First use inside a stream capture is refused (call ab200_init() - or any
+// eager launch - before capturing).
+struct DeviceOnce {
+  std::atomic<int> done[kMaxDevices];
+  std::mutex mu;
+};
+template <typename F>
+inline int device_once(DeviceOnce& o, cudaStream_t s, const char* what, F&& fill) {
+  int dev = 0;
+  AB200_CUDA_OK(cudaGetDevice(&dev));
+  AB200_REQUIRE(dev >= 0 && dev < kMaxDevices, AB200_E_INVALID, "device ordinal %d out of range", dev);
+  if (o.done[dev].load(std::memory_order_acquire)) return AB200_OK;
+  std::lock_guard<std::mutex> lock(o.mu);
+  if (o.done[dev].load(std::memory_order_acquire)) return AB200_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  AB200_CUDA_OK(cudaStreamIsCapturing(s, &cap));
+  AB200_REQUIRE(cap == cudaStreamCaptureStatusNone, AB200_E_INVALID,
+                "%s: first use on device %d inside a stream capture - call ab200_init() before capturing",
+                what, dev);
+  int rc = fill(s);
+  if (rc != AB200_OK) return rc;
+  AB200_CUDA_OK(cudaStreamSynchronize(s));
+  o.done[dev].store(1, std::memory_order_release);
+  return AB200_OK;
+}
+// cudaFuncSetAttribute(max dynamic smem) once per (kernel, device); racing callers are harmless
+template <typename K>
+inline int ensure_max_smem(K kernel, std::atomic<bool> (&flags)[kMaxDevices], int bytes) {
+  int dev = 0;
+  AB200_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !flags[dev].load(std::memory_order_acquire)) {
+    AB200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < kMaxDevices) flags[dev].store(true, std::memory_order_release);
+  }
+  return AB200_OK;
+}
+// per-translation-unit initialisers called by ab200_init()
+int init_lstm_tables(cudaStream_t s);
+int init_mlp_tables(cudaStream_t s);
+int init_gemm_kernels();
 
 struct LaunchCfg {
   cudaLaunchConfig_t cfg;

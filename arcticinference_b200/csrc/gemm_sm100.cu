@@ -234,17 +234,47 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
   const uint32_t flag_slot = tmem_slot + 8u;
 
+  const int num_kb = p.num_k_blocks;
+  const int my_tiles = static_cast<int>(blockIdx.x) < p.num_n_tiles
+                           ? (p.num_n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
+  // producer's view: linearised (tile, k-block) sequence of this CTA
+  const int total = my_tiles * num_kb;
+  auto n0_of = [&](int g) { return (static_cast<int>(blockIdx.x) + (g / num_kb) * static_cast<int>(gridDim.x)) * p.block_n; };
+  auto load_x = [&](int g, int stage) {
+    const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+    for (int t = 0; t < MT; ++t)
+      tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
+  };
+  auto load_w = [&](int g, int stage) {
+    const uint32_t sa = smem_base + stage * stage_bytes;
+    tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
+  };
+  const int pre = total < p.pre_stages ? total : p.pre_stages;
+
   if (warp == 0 && lane == 0) {
     trace_stamp(p.trace, 0);
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    // The producer owns the stage barriers and starts streaming right away: the weights do not depend
+    // on the previous kernel, so the ring is filled with W (and L2 warmed with the k-blocks after
+    // that) while warp 1 is still allocating TMEM and long BEFORE the dependency wait.
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    fence_mbar_init();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int g = 0; g < pre; ++g) {
+      mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
+      load_w(g, g);
+    }
+    const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
+    for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < stages; ++s) {
-        mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), 1);
-      }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
@@ -266,34 +296,9 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   // load, so that the dependent's launch overlaps just the tail of this kernel.
   if (!p.late_trigger) pdl_launch_dependents();
 
-  const int num_kb = p.num_k_blocks;
-  const int my_tiles = static_cast<int>(blockIdx.x) < p.num_n_tiles
-                           ? (p.num_n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
-                           : 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const int total = my_tiles * num_kb;   // linearised (tile, k-block) sequence of this CTA
-      auto n0_of = [&](int g) { return (static_cast<int>(blockIdx.x) + (g / num_kb) * static_cast<int>(gridDim.x)) * p.block_n; };
-      auto load_x = [&](int g, int stage) {
-        const uint32_t sa = smem_base + stage * stage_bytes;
-#pragma unroll
-        for (int t = 0; t < MT; ++t)
-          tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
-      };
-      auto load_w = [&](int g, int stage) {
-        const uint32_t sa = smem_base + stage * stage_bytes;
-        tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
-      };
-      // The weights do not depend on the previous kernel: fill the ring with W (and warm L2 with
-      // the k-blocks after that) BEFORE waiting for the producer of x.
-      const int pre = total < p.pre_stages ? total : p.pre_stages;
-      for (int g = 0; g < pre; ++g) {
-        mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
-        load_w(g, g);
-      }
-      const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
-      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
       pdl_wait();
       trace_stamp(p.trace, 1);
       for (int g = 0; g < pre; ++g) load_x(g, g);
@@ -748,17 +753,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // magic static: initialised exactly once, thread-safe
+  static const EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
+    EncodeTiledFn f = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
+      f = reinterpret_cast<EncodeTiledFn>(p);
     (void)cudaGetLastError();
-  }
+    return f;
+  }();
   return fn;
 }
 
@@ -782,16 +787,40 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K
   return AB200_OK;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-    (void)cudaGetLastError();
+static int sm_count() { return device_sm_count(); }
+
+// Tensor maps depend only on (base, rows, K, ld, box rows, element size), never on the contents, so a
+// cached map stays valid for as long as those match: a small per-thread cache removes the two driver
+// encode calls from every eager launch (graph replays never reach this code).
+struct TmapKey {
+  const void* base;
+  int64_t rows, K, ld;
+  int32_t box_rows, esize;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows && esize == o.esize;
   }
-  return n;
+};
+struct TmapCache {
+  static constexpr int kEntries = 32;
+  TmapKey keys[kEntries];
+  alignas(64) CUtensorMap maps[kEntries];
+  int used = 0, next = 0;
+};
+static int get_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                    int esize) {
+  static thread_local TmapCache cache;
+  const TmapKey key{base, rows, K, ld, box_rows, esize};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.keys[i] == key) {
+      *map = cache.maps[i];
+      return AB200_OK;
+    }
+  int rc = make_tmap(map, base, rows, K, ld, box_rows, esize);
+  if (rc != AB200_OK) return rc;
+  const int slot = cache.used < TmapCache::kEntries ? cache.used++ : (cache.next++ % TmapCache::kEntries);
+  cache.keys[slot] = key;
+  cache.maps[slot] = *map;
+  return AB200_OK;
 }
 
 // Tile width: minimise waves * (block_n + fixed per-tile cost) so the tile count lands just under
@@ -811,29 +840,6 @@ int pick_block_n(int64_t N, int sms, int max_bn) {
   return best_bn;
 }
 
-static int env_int(const char* name, int dflt);
-}  // namespace ab200
-// Rows that share one pass over the weights.  256 (MT <= 2, block_n <= 128) by default: at 512
-// rows the MT = 4 variant is left with 64-column tiles and becomes bound by the L2 -> SM ingest
-// of the activation tiles (measured 568 us vs 2 x 222 us for the 8B head); AB200_ROWS_PER_PASS=512
-// re-enables it.
-int ab200::gemm_late_trigger() {
-  static const int v = env_int("AB200_LATE_TRIGGER", 1);
-  return v;
-}
-int ab200::gemm_rows_per_pass() {
-  static const int v = [] {
-    const int e = env_int("AB200_ROWS_PER_PASS", 256);
-    return e >= 512 ? 512 : (e >= 256 ? 256 : 128);
-  }();
-  return v;
-}
-namespace ab200 {
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 struct ArgmaxExtra {
   unsigned long long* packed = nullptr;
   int64_t* tokens_out = nullptr;
@@ -848,35 +854,33 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
                             int64_t ldo, const ArgmaxExtra& ax, cudaStream_t s) {
   // function attributes are per device: one flag per device ordinal (one process may drive several)
-  static bool attr_set[64] = {};
-  int dev = 0;
-  AB200_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100<EPI, MT, KIND>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  static std::atomic<bool> attr_set[kMaxDevices];
+  int rc = ensure_max_smem(gemm_tn_sm100<EPI, MT, KIND>, attr_set, kSmemLimit);
+  if (rc != AB200_OK) return rc;
   const int sms = sm_count();
-  const int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
+  int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
+  const int forced_bn = EPI == EPI_STORE ? tune().gate_block_n : tune().head_block_n;
+  if (forced_bn >= 16 && forced_bn <= kMaxBlockN / MT && forced_bn % 16 == 0) bn = forced_bn;   // debug sweeps only
   const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
   const int box_m = MT == 1 ? static_cast<int>((m_rows + 7) / 8 * 8) : kTileM;
   // weight bytes in flight per SM = stages x tile: with a 7-stage ring the 8B gate GEMM was bound by
   // (bytes in flight) / (HBM latency) = 56-61 GB/s per SM, not by HBM - the activation slot is
   // therefore sized to the rows the batch really has
   // (the MMA reads all M rows of the slot, valid or not: M = 64 -> 8 KiB, M = 128 -> 16 KiB)
-  const bool m64 = MT == 1 && m_rows <= 64 && env_int("AB200_UMMA_M64", 1);
+  const bool m64 = MT == 1 && m_rows <= 64 && tune().umma_m64;
   const uint32_t a_slot = m64 ? 64u * 128u : MT * kABytes;
   const uint32_t stage_bytes = a_slot + bn * 128;
   int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (tune().max_stages >= 2 && stages > tune().max_stages) stages = tune().max_stages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
 
   constexpr int esize = KIND == KIND_BF16 ? 2 : 1;
   constexpr int k_elems = kRowBytes / esize;
   CUtensorMap tmx, tmw;
-  int rc = make_tmap(&tmx, x, m_rows, K, ldx, box_m, esize);
+  rc = get_tmap(&tmx, x, m_rows, K, ldx, box_m, esize);
   if (rc != AB200_OK) return rc;
-  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn, esize);
+  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn, esize);
   if (rc != AB200_OK) return rc;
 
   GemmParams p;
@@ -886,9 +890,9 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.num_n_tiles = num_n_tiles;
   p.num_k_blocks = static_cast<int32_t>((K + k_elems - 1) / k_elems);
   p.stages = stages;
-  p.l2_prefetch_kb = pdl_enabled() ? env_int("AB200_L2_PREFETCH_KB", 0) : 0;
+  p.l2_prefetch_kb = pdl_enabled() ? tune().l2_prefetch_kb : 0;
   p.late_trigger = gemm_late_trigger();
-  p.pre_stages = env_int("AB200_PRE_STAGES", stages);
+  p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
   if (p.pre_stages < 0) p.pre_stages = 0;
   p.tx_bytes = static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
@@ -923,14 +927,9 @@ template <int EPI>
 static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
                                  int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out, int64_t ldo,
                                  const ArgmaxExtra& ax, cudaStream_t s) {
-  static bool attr_set[64] = {};
-  int dev = 0;
-  AB200_CUDA_OK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    AB200_CUDA_OK(cudaFuncSetAttribute(gemm_tn_sm100_2cta<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmemLimit));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  static std::atomic<bool> attr_set[kMaxDevices];
+  int rc = ensure_max_smem(gemm_tn_sm100_2cta<EPI>, attr_set, kSmemLimit);
+  if (rc != AB200_OK) return rc;
   const int pairs = sm_count() / 2;
   // tile width: multiple of 32 (each CTA holds half of it), balanced over the CTA pairs
   int bn = 32;
@@ -950,9 +949,9 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   if (stages > kMaxStages) stages = kMaxStages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
   CUtensorMap tmx, tmw;
-  int rc = make_tmap(&tmx, x, m_rows, K, ldx, kTileM, 2);
+  rc = get_tmap(&tmx, x, m_rows, K, ldx, kTileM, 2);
   if (rc != AB200_OK) return rc;
-  rc = make_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2);
+  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2);
   if (rc != AB200_OK) return rc;
   GemmParams p;
   p.m_rows = static_cast<int32_t>(m_rows);
@@ -963,9 +962,8 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.stages = stages;
   p.l2_prefetch_kb = 0;
   p.late_trigger = gemm_late_trigger();
-  p.pre_stages = env_int("AB200_PRE_STAGES", stages);
+  p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
-  if (p.pre_stages < 0) p.pre_stages = 0;
   p.m64 = 0;
   p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u);   // both CTAs
   // instruction descriptor: D = f32, A/B = bf16, K-major, N >> 3, M = 256 >> 4
@@ -1014,7 +1012,7 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
     int rc;
     if (rows <= kTileM)
       rc = launch_gemm_pass<EPI, 1, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
-    else if (rows <= 2 * kTileM && KIND == KIND_BF16 && env_int("AB200_GEMM_2CTA", 1))
+    else if (rows <= 2 * kTileM && KIND == KIND_BF16 && tune().gemm_2cta)
       rc = launch_gemm_pass_2cta<EPI>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else if (rows <= 2 * kTileM)
       rc = launch_gemm_pass<EPI, 2, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
@@ -1022,6 +1020,23 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
       rc = launch_gemm_pass<EPI, 4, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     if (rc != AB200_OK) return rc;
   }
+  return AB200_OK;
+}
+
+// ab200_init(): set the shared-memory attribute of every tcgen05 instantiation on the current device
+// (so that no first-use attribute call can land inside a stream capture) and resolve the driver's
+// tensor-map encoder.
+int init_gemm_kernels() {
+  AB200_REQUIRE(get_encode_fn() != nullptr, AB200_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+#define AB200_INIT_ATTR(...)                                                                              \
+  AB200_CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit))
+  AB200_INIT_ATTR(gemm_tn_sm100<EPI_STORE, 1, KIND_BF16>);
+  AB200_INIT_ATTR(gemm_tn_sm100<EPI_ARGMAX, 1, KIND_BF16>);
+  AB200_INIT_ATTR(gemm_tn_sm100<EPI_STORE, 1, KIND_FP8>);
+  AB200_INIT_ATTR(gemm_tn_sm100<EPI_ARGMAX, 1, KIND_FP8>);
+  AB200_INIT_ATTR(gemm_tn_sm100_2cta<EPI_STORE>);
+  AB200_INIT_ATTR(gemm_tn_sm100_2cta<EPI_ARGMAX>);
+#undef AB200_INIT_ATTR
   return AB200_OK;
 }
 

@@ -470,6 +470,7 @@ sum_lstm_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ gates, int64_t ldg
   if (threadIdx.x == 0) trace_stamp(trace, 2);
 }
 
+#ifdef AB200_DEBUG
 // bf16 unary functions of the bit-exact emulation on arbitrary inputs (test hook: all 65 536
 // values).  fast/exact: bf16 results of the shortcut / of ATen's formula; fast32/exact32
 // (optional): the unguarded fast approximation and ATen's value in fp32, to measure the guard.
@@ -564,8 +565,23 @@ __global__ void gelu_search_kernel(const float* __restrict__ cand, uint32_t* __r
   }
 }
 
-// debug switch (ab200_debug_cell_generic): 1 = run the generic kernel also for bf16 + emulation
-static int g_cell_generic = 0;
+#endif  // AB200_DEBUG
+
+// debug switch (ab200_debug_cell_generic, debug flavour only): 1 = run the generic kernel also for
+// bf16 + emulation
+#ifdef AB200_DEBUG
+static std::atomic<int> g_cell_generic{0};
+#else
+static constexpr int g_cell_generic = 0;
+#endif
+static DeviceOnce g_gelu_tab_once;
+int init_lstm_tables(cudaStream_t s) {
+  return device_once(g_gelu_tab_once, s, "GELU table", [](cudaStream_t st) {
+    gelu_lut_init_kernel<<<kGeluTabEntries / 256, 256, 0, st>>>();
+    AB200_CHECK_LAUNCH("gelu_lut_init_kernel");
+    return AB200_OK;
+  });
+}
 // block size / items-per-thread for a row of `nvec` 16-byte vectors
 static bool row_launch_shape(int64_t nvec, int* threads, int* items) {
   for (int it : {1, 2, 4}) {
@@ -631,21 +647,10 @@ static int launch_cell(const void* gates, int64_t ldg, const void* emb, const in
       vocab, alpha, eps, a_clear, a_cnt, a_trace, a_sq, state_scale
   if constexpr (EMU && std::is_same<T, __nv_bfloat16>::value) {
     if (!g_cell_generic) {
-      // first use on this device: fill the GELU table; this one cell launch is then fully
-      // stream-serialised (no PDL) because the kernel reads the table before its dependency wait
-      static bool lut_ready[64] = {};
-      int dev = 0;
-      AB200_CUDA_OK(cudaGetDevice(&dev));
-      if (dev < 0 || dev >= 64 || !lut_ready[dev]) {
-        gelu_lut_init_kernel<<<kGeluTabEntries / 256, 256, 0, s>>>();
-        AB200_CHECK_LAUNCH("gelu_lut_init_kernel");
-        lc.cfg.numAttrs = 0;
-        // under stream capture the fill only runs when the graph is replayed: keep filling until an
-        // eager launch has really executed it
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        (void)cudaStreamIsCapturing(s, &cap);
-        if (dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone) lut_ready[dev] = true;
-      }
+      // first use on this device: fill the GELU table (once, synchronously, under a mutex - the
+      // kernel reads the table before its dependency wait, so it must be complete before ANY launch)
+      int rc = init_lstm_tables(s);
+      if (rc != AB200_OK) return rc;
       // <= 512 threads per row (D <= 4096): 40 registers so that three CTAs share an SM
       const float inv_d = 1.0f / static_cast<float>(D);
       const bool full = D == 8LL * items * threads;
@@ -769,10 +774,9 @@ extern "C" int32_t ab200_sum_lstm_cell(const void* gates, int64_t gates_row_stri
 #undef AB200_ARGS
 }
 
+#ifdef AB200_DEBUG
 extern "C" int32_t ab200_debug_cell_generic(int32_t on) {
-  const int32_t prev = g_cell_generic;
-  g_cell_generic = on != 0;
-  return prev;
+  return g_cell_generic.exchange(on != 0);
 }
 
 extern "C" int32_t ab200_debug_sigmoid_search(const float* candidates, int32_t n_candidates,
@@ -800,3 +804,4 @@ extern "C" int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16
   AB200_CHECK_LAUNCH("unary_bf16_kernel");
   return AB200_OK;
 }
+#endif  // AB200_DEBUG

@@ -213,7 +213,19 @@ sum_mlp_cell_bf16x2_kernel(const __nv_bfloat16* __restrict__ pre, int64_t ldp,
   if (threadIdx.x == 0) trace_stamp(trace, 2);
 }
 
-static int g_mlp_generic = 0;
+#ifdef AB200_DEBUG
+static std::atomic<int> g_mlp_generic{0};
+#else
+static constexpr int g_mlp_generic = 0;
+#endif
+static DeviceOnce g_gelu_lut_mlp_once;
+int init_mlp_tables(cudaStream_t s) {
+  return device_once(g_gelu_lut_mlp_once, s, "GELU table (MLP)", [](cudaStream_t st) {
+    gelu_lut_init_mlp_kernel<<<1, kGeluLutSize, 0, st>>>();
+    AB200_CHECK_LAUNCH("gelu_lut_init_mlp_kernel");
+    return AB200_OK;
+  });
+}
 
 static bool mlp_row_shape(int64_t nvec, int* threads, int* items) {
   for (int it : {1, 2, 4}) {
@@ -255,19 +267,8 @@ static int launch_mlp(const void* pre, int64_t ldp, const void* emb, const int64
       a_clear, a_cnt, a_trace, a_sq, state_scale
   if constexpr (EMU && std::is_same<T, __nv_bfloat16>::value) {
     if (!g_mlp_generic) {
-      static bool lut_ready[64] = {};
-      int dev = 0;
-      AB200_CUDA_OK(cudaGetDevice(&dev));
-      if (dev < 0 || dev >= 64 || !lut_ready[dev]) {
-        gelu_lut_init_mlp_kernel<<<1, kGeluLutSize, 0, s>>>();
-        AB200_CHECK_LAUNCH("gelu_lut_init_mlp_kernel");
-        lc.cfg.numAttrs = 0;   // this launch reads the table before its dependency wait
-        // under stream capture the fill only runs when the graph is replayed: keep filling until an
-        // eager launch has really executed it
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        (void)cudaStreamIsCapturing(s, &cap);
-        if (dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone) lut_ready[dev] = true;
-      }
+      int rc = init_mlp_tables(s);   // first use on this device: fill the GELU table (synchronous, once)
+      if (rc != AB200_OK) return rc;
 #define AB200_MLP_FAST(IT)                                                                     \
   do {                                                                                         \
     if (guard)                                                                                 \
@@ -332,11 +333,9 @@ __global__ void mlp_unpack_steps_kernel(const unsigned long long* __restrict__ p
 
 using namespace ab200;
 
-extern "C" int32_t ab200_debug_mlp_generic(int32_t on) {
-  const int32_t prev = g_mlp_generic;
-  g_mlp_generic = on != 0;
-  return prev;
-}
+#ifdef AB200_DEBUG
+extern "C" int32_t ab200_debug_mlp_generic(int32_t on) { return g_mlp_generic.exchange(on != 0); }
+#endif
 
 extern "C" int32_t ab200_sum_mlp_cell(const void* pre, int64_t pre_row_stride, const void* emb_table,
                                       const int64_t* tokens, const uint64_t* packed_argmax,

@@ -22,19 +22,33 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
-static unsigned long long* g_trace_base = nullptr;
-static int g_trace_cap = 0, g_trace_next = 0;
+// trace state: per host thread (a profiling thread traces its own launches, nobody else's)
+static thread_local unsigned long long* g_trace_base = nullptr;
+static thread_local int g_trace_cap = 0, g_trace_next = 0;
 unsigned long long* next_trace_slot() {
   if (g_trace_base == nullptr || g_trace_next >= g_trace_cap) return nullptr;
   return g_trace_base + 4 * static_cast<size_t>(g_trace_next++);
 }
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AB200_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+#ifdef AB200_DEBUG
+Tune& tune_mut() {
+  static Tune t;
+  return t;
+}
+#endif
+int device_sm_count() {
+  static std::atomic<int> cached[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    (void)cudaGetLastError();
+    return 148;
   }
-  return v == 1;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    (void)cudaGetLastError();
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 // tokens_out[b * S + s] = token of packed[s * B + b]
@@ -108,7 +122,34 @@ static Workspace plan(const ab200_lstm_speculator* sp, int64_t B, int32_t S) {
 using namespace ab200;
 
 extern "C" const char* ab200_last_error(void) { return g_err; }
-extern "C" int32_t ab200_abi_version(void) { return 4; }
+extern "C" int32_t ab200_abi_version(void) { return 5; }
+extern "C" int32_t ab200_init(void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  (void)device_sm_count();
+  int rc = init_gemm_kernels();
+  if (rc != AB200_OK) return rc;
+  rc = init_lstm_tables(s);
+  if (rc != AB200_OK) return rc;
+  return init_mlp_tables(s);
+}
+#ifdef AB200_DEBUG
+extern "C" int32_t ab200_debug_set_tunable(const char* name, int32_t value) {
+  AB200_REQUIRE(name != nullptr, AB200_E_INVALID, "debug_set_tunable: NULL name");
+  Tune& t = tune_mut();
+  struct { const char* n; int* p; } tab[] = {
+      {"pdl", &t.pdl}, {"umma_m64", &t.umma_m64}, {"gemm_2cta", &t.gemm_2cta},
+      {"rows_per_pass", &t.rows_per_pass}, {"late_trigger", &t.late_trigger},
+      {"pre_stages", &t.pre_stages}, {"l2_prefetch_kb", &t.l2_prefetch_kb},
+      {"gate_block_n", &t.gate_block_n}, {"head_block_n", &t.head_block_n},
+      {"max_stages", &t.max_stages}, {"early_producer", &t.early_producer}, {"dyn_tiles", &t.dyn_tiles}};
+  for (auto& e : tab)
+    if (strcmp(e.n, name) == 0) {
+      *e.p = value;
+      return AB200_OK;
+    }
+  AB200_REQUIRE(false, AB200_E_INVALID, "debug_set_tunable: unknown tunable '%s'", name);
+}
+#endif
 extern "C" int64_t ab200_launch_count(void) { return g_launches; }
 extern "C" int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches) {
   g_trace_base = reinterpret_cast<unsigned long long*>(device_slots);

@@ -32,7 +32,7 @@ class ArcticMLPSpeculator:
                  max_num_seqs: int = 256, dtype: torch.dtype = torch.bfloat16,
                  device: str | torch.device = "cuda", scale_input: bool = True,
                  enforce_eager: bool = False, emulate_eager_rounding: bool | int = True,
-                 alpha_flavor: str = "cuda", quantize_lm_head: bool = False,
+                 alpha_flavor: str = "cuda", quantize_lm_head: Optional[bool] = None,
                  fp8_head_max_batch: int = 32) -> None:
         self._lib = _capi.lib()
         if dtype not in (torch.bfloat16, torch.float32):
@@ -41,6 +41,8 @@ class ArcticMLPSpeculator:
         if inner_dim % 8 or emb_dim % 8:
             raise ValueError("inner_dim and emb_dim must be multiples of 8")
         self.device = torch.device(device)
+        if self.device.type == "cuda":
+            _capi.init_device(self.device)   # function attributes + constant tables, before any capture
         self.dtype = dtype
         self.n_predict = n_predict
         self.vocab_size = vocab_size
@@ -64,8 +66,13 @@ class ArcticMLPSpeculator:
             raise ValueError("alpha_flavor must be 'cuda' or 'cpu'")
         self.alpha = float(alpha)
         self.eps = 1e-6
-        self.quantize_lm_head = bool(quantize_lm_head) and dtype == torch.bfloat16 and inner_dim % 16 == 0
+        # The reference hard-codes quantize_lm_head = True and builds `qhead` for tied weights only
+        # (arctic_speculator.py:129, 162-173), used for batch <= 32 (:298-299): None = exactly that.
+        fp8_ok = dtype == torch.bfloat16 and inner_dim % 16 == 0 and self.device.type == "cuda"
+        self.quantize_lm_head = (fp8_ok and tie_weights) if quantize_lm_head is None \
+            else (bool(quantize_lm_head) and fp8_ok)
         self.fp8_head_max_batch = fp8_head_max_batch
+        self._graph_epoch = 0
 
         D, H, V, n = inner_dim, emb_dim, vocab_size, self.max_speculative_tokens
         Vp = pad_vocab_size(V)
@@ -96,6 +103,27 @@ class ArcticMLPSpeculator:
         }
         self._workspace: Optional[torch.Tensor] = None
         self._desc: Optional[_capi.MlpSpeculatorDesc] = None
+        if self.quantize_lm_head:
+            # allocated ONCE: captured graphs bake these pointers in (re-quantised in place on reload)
+            for i in range(n_sets):
+                self._head_q[i] = torch.zeros(Vp, D, dtype=torch.uint8, device=self.device)
+                self._head_scale[i] = torch.ones(1, dtype=torch.float32, device=self.device)
+
+    @property
+    def qhead(self):
+        """FP8 heads {index: ([V_pad, D] e4m3 as uint8, scale [1])} or None; assigning None disables
+        them (the bf16-oracle recipe `model.qhead = None`)."""
+        return None if not self._head_q else {i: (q, self._head_scale[i]) for i, q in self._head_q.items()}
+
+    @qhead.setter
+    def qhead(self, value) -> None:
+        if value is not None:
+            raise ValueError("qhead can only be disabled (set to None); it is rebuilt from head.N.weight")
+        self.quantize_lm_head = False
+        self._head_q, self._head_scale = {}, {}
+        self._desc = None
+        self.cuda_graphs.clear()
+        self._graph_epoch += 1
 
     # ---- parameters ---------------------------------------------------------------------------
     def named_parameters(self):
@@ -127,19 +155,16 @@ class ArcticMLPSpeculator:
             self._quantize_heads()
 
     def _quantize_heads(self) -> None:
-        self._head_q.clear()
-        self._head_scale.clear()
-        for i in range(1 if self.tie_weights else self.max_speculative_tokens):
+        """IN PLACE into the buffers allocated at construction: graphs captured before a second
+        load_weights() keep reading valid, freshly quantised heads."""
+        for i in sorted(self._head_q):
             head = self._params[f"head.{i}.weight"]
-            q = torch.empty(head.shape, dtype=torch.uint8, device=self.device)
-            s = torch.zeros(1, dtype=torch.float32, device=self.device)
+            q, s = self._head_q[i], self._head_scale[i]
             with torch.cuda.device(self.device):
                 _capi.check(self._lib.ab200_fp8_quantize_weight(
                     head.data_ptr(), q.data_ptr(), s.data_ptr(), head.shape[0], head.shape[1],
                     head.stride(0), q.stride(0), _capi.current_stream_ptr(self.device)),
                     "ab200_fp8_quantize_weight")
-            self._head_q[i], self._head_scale[i] = q, s
-        self._desc = None
 
     # ---- native descriptor / workspace -------------------------------------------------------
     def _descriptor(self) -> _capi.MlpSpeculatorDesc:

@@ -61,7 +61,7 @@ class ArcticLSTMSpeculator:
                  dtype: torch.dtype = torch.bfloat16, device: str | torch.device = "cuda",
                  scale_input: bool = True, enforce_eager: bool = False,
                  emulate_eager_rounding: bool | int = True, alpha_flavor: str = "cuda",
-                 quantize_lm_head: bool = False, fp8_head_max_batch: int = 32,
+                 quantize_lm_head: Optional[bool] = None, fp8_head_max_batch: int = 32,
                  tp_size: int = 1, tp_rank: int = 0, tp_group=None) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
         # Tensor parallelism of the vocab head (the reference shards ParallelLMHead over
@@ -75,6 +75,9 @@ class ArcticLSTMSpeculator:
         if inner_dim % 8 or input_hidden_dim % 8:
             raise ValueError("inner_dim and input_hidden_dim must be multiples of 8")
         self.device = torch.device(device)
+        if self.device.type == "cuda":
+            # function attributes + constant tables of this device, before any graph capture
+            _capi.init_device(self.device)
         self.dtype = dtype
         self.n_predict = n_predict
         self.vocab_size = vocab_size
@@ -103,13 +106,21 @@ class ArcticLSTMSpeculator:
             raise ValueError("alpha_flavor must be 'cuda' or 'cpu'")
         self.alpha = float(alpha)
         self.eps = 1e-6
-        # FP8 duplicate of the head, used iff the (padded) batch <= 32 - the reference's `qhead`
-        # (arctic_speculator.py:436, 455-465, 726-727).  Off by default here: its parity is pinned
-        # to vLLM 0.22's fp8 ops, not to the reference's vLLM 0.9.2 binary.
-        self.quantize_lm_head = bool(quantize_lm_head) and dtype == torch.bfloat16 and inner_dim % 16 == 0
+        # FP8 duplicate of the head, used iff the (padded) batch <= 32 - the reference's `qhead`.
+        # The reference hard-codes `self.quantize_lm_head = True` (arctic_speculator.py:435) and picks
+        # `qhead` for batch_size <= 32 (:726-727), so that is the default here too (None = "as the
+        # reference": on wherever it is built - bf16, D % 16 == 0, tp_size == 1).  Its arithmetic is
+        # pinned to vLLM 0.22's fp8 ops, not to the reference's vLLM 0.9.2 binary (DESIGN.md section
+        # 2); the bf16-oracle recipe of SURVEY App. C (`model.qhead = None`) works here unchanged.
+        fp8_ok = dtype == torch.bfloat16 and inner_dim % 16 == 0 and tp_size == 1 and self.device.type == "cuda"
+        if quantize_lm_head and tp_size > 1:
+            raise ValueError("the FP8 head is not built for tp_size > 1")
+        self.quantize_lm_head = fp8_ok if quantize_lm_head is None else (bool(quantize_lm_head) and fp8_ok)
         self.fp8_head_max_batch = fp8_head_max_batch
         self._head_q: Optional[torch.Tensor] = None
         self._head_scale: Optional[torch.Tensor] = None
+        # bumped whenever something baked into captured graphs changes (cached plans check it)
+        self._graph_epoch = 0
 
         D, H, V = inner_dim, input_hidden_dim, vocab_size
         Vp = pad_vocab_size(V)
@@ -117,8 +128,6 @@ class ArcticLSTMSpeculator:
             raise ValueError("padded vocab size must be divisible by tp_size")
         self.vocab_padded = Vp
         self.vocab_per_rank = Vp // tp_size          # num_embeddings_per_partition
-        if tp_size > 1 and quantize_lm_head:
-            raise ValueError("the FP8 head is not built for tp_size > 1")
         mk = lambda *shape: torch.zeros(*shape, dtype=dtype, device=self.device)
         self._params: Dict[str, torch.Tensor] = collections.OrderedDict([
             ("head.0.weight", mk(self.vocab_per_rank, D)),
@@ -142,10 +151,42 @@ class ArcticLSTMSpeculator:
         }
         self._workspace: Optional[torch.Tensor] = None
         self._desc: Optional[_capi.LstmSpeculatorDesc] = None
+        if self.quantize_lm_head:
+            # allocated ONCE: captured graphs bake these pointers in, so re-loading weights must
+            # re-quantise into the same buffers
+            self._head_q = torch.zeros(self.vocab_per_rank, D, dtype=torch.uint8, device=self.device)
+            self._head_scale = torch.ones(1, dtype=torch.float32, device=self.device)
 
     # ---- parameters ---------------------------------------------------------------------------
     def named_parameters(self):
         return list(self._params.items())
+
+    @property
+    def qhead(self):
+        """The FP8 head ([V_pad, D] e4m3 as uint8, scale [1] f32) or None.  Assigning None disables it
+        (the reference's oracle recipe `model.qhead = None`: bf16 head at every batch size)."""
+        return None if self._head_q is None else (self._head_q, self._head_scale)
+
+    @qhead.setter
+    def qhead(self, value) -> None:
+        if value is not None:
+            raise ValueError("qhead can only be disabled (set to None); it is rebuilt from head.0.weight")
+        self.quantize_lm_head = False
+        self._head_q = self._head_scale = None
+        self._invalidate_graphs()
+
+    def _invalidate_graphs(self) -> None:
+        """Drop everything that baked device pointers / kernel choices in: descriptor, graphs, plans."""
+        self._desc = None
+        self.cuda_graphs.clear()
+        self._graph_epoch += 1
+
+    def uses_fp8_head(self, batch_size: int) -> bool:
+        """The reference's selection rule (arctic_speculator.py:726-727): `qhead` iff it exists and the
+        batch the loop runs on (the PADDED batch under CUDA graphs, :631-640) is <= 32."""
+        b = padding_size(batch_size) if (self.cuda_graph_mode and batch_size <= self.cuda_graph_max_batch_size) \
+            else batch_size
+        return self._head_q is not None and b <= self.fp8_head_max_batch
 
     def _set_param(self, name: str, value: torch.Tensor) -> None:
         p = self._params[name]
@@ -176,7 +217,7 @@ class ArcticLSTMSpeculator:
                 weights[name] = torch.cat([weights.pop(p) for p in parts])
         for name, w in weights.items():
             if name.startswith("qhead"):
-                continue  # FP8 duplicate head: out of scope
+                continue  # rebuilt from head.0.weight below (the reference loads head into qhead, :899-902)
             if name in self._params:
                 self._set_param(name, w.to(device=self.device, dtype=self.dtype))
         self._desc = None
@@ -185,16 +226,14 @@ class ArcticLSTMSpeculator:
 
     def _quantize_head(self) -> None:
         """process_weights_after_loading of the reference's qhead (fp8.py:207-221): dynamic
-        per-tensor e4m3 quantisation of the (padded) head weight."""
+        per-tensor e4m3 quantisation of the (padded) head weight - IN PLACE into the buffers the
+        captured graphs point at, so a second load_weights() keeps every graph valid."""
         head = self._params["head.0.weight"]
-        self._head_q = torch.empty(head.shape, dtype=torch.uint8, device=self.device)
-        self._head_scale = torch.zeros(1, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _capi.check(self._lib.ab200_fp8_quantize_weight(
                 head.data_ptr(), self._head_q.data_ptr(), self._head_scale.data_ptr(), head.shape[0],
                 head.shape[1], head.stride(0), self._head_q.stride(0),
                 _capi.current_stream_ptr(self.device)), "ab200_fp8_quantize_weight")
-        self._desc = None
 
     # ---- native descriptor / workspace -------------------------------------------------------
     def _descriptor(self) -> _capi.LstmSpeculatorDesc:
@@ -472,6 +511,9 @@ class ArcticProposer:
         if max_gen_len == 1:                                              # :134-136
             return sample_hidden_states
         assert num_draft_tokens is not None
+        # the reference passes spec_decode_metadata (arctic_proposer.py:113-119) and reads its
+        # .num_draft_tokens (:139); a plain host list is accepted as well
+        num_draft_tokens = getattr(num_draft_tokens, "num_draft_tokens", num_draft_tokens)
         R = sampled_token_ids.shape[0]
         h = sample_hidden_states
         if h.stride(-1) != 1:
@@ -497,8 +539,11 @@ class ArcticProposer:
         # Steady state first: the hidden-state H2D copy is the long pole of the call (0.5 MB over PCIe), so it is
         # enqueued before ANY other host work; everything below overlaps with it.
         plan = self._plans.get((previous_hidden_states.shape[0], S)) if previous_hidden_states.dim() == 2 else None
+        if plan is not None and plan[-1] != m._graph_epoch:
+            self._plans.clear()              # graphs were invalidated (e.g. qhead switched off): re-plan
+            plan = None
         if plan is not None and previous_hidden_states.shape[1] == m.input_hidden_dim:
-            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np = plan
+            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np, _ = plan
             hid_dev.copy_(previous_hidden_states, non_blocking=True)
             ids = torch.as_tensor(context_token_ids)
             if ids.dim() == 1 and ids.shape[0] == hid_dev.shape[0]:
@@ -534,9 +579,9 @@ class ArcticProposer:
                 out_dev = bufs["next_tokens"].view(-1)[:padded * S].view(padded, S)[:B]
                 out = self._out_pinned[:B * S].view(B, S)
                 plan = (bufs["previous_hidden_states"][:B], bufs["last_tokens"][:B], self._ids_pinned[:B],
-                        self._ids_pinned.numpy()[:B], graph, out_dev, out, out.numpy())
+                        self._ids_pinned.numpy()[:B], graph, out_dev, out, out.numpy(), m._graph_epoch)
                 self._plans[(B, S)] = plan
-            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np = plan
+            hid_dev, ids_dev, ids_pin, ids_np, graph, out_dev, out, out_np, _ = plan
             hid_dev.copy_(previous_hidden_states, non_blocking=True)
             if ids.device.type == "cpu":
                 ids_np[:] = ids.numpy()

@@ -46,11 +46,19 @@ AB200_API int32_t ab200_abi_version(void);
 /* Number of kernel launches this library has enqueued on this thread since load (bench claim). */
 AB200_API int64_t ab200_launch_count(void);
 
+/* One-time per-device initialisation for the CURRENT device: shared-memory attributes of the tcgen05
+ * kernels, the constant tables of the cell kernels (filled on `stream`, which is then synchronised)
+ * and the cached SM count.  Thread-safe and idempotent.  Every entry point also initialises lazily
+ * on first use, but a first use inside a CUDA stream capture is refused (AB200_E_INVALID): call this
+ * once per device before capturing graphs (the host classes do, at construction). */
+AB200_API int32_t ab200_init(void* stream);
+
 /* Device-side timeline for profiling a (graph-captured) draft loop.  device_slots: 4 uint64 per
  * traced launch, initialised by the caller to {~0, ~0, 0, 0}; each speculator kernel launched while
  * tracing is on takes the next slot and records %globaltimer ns: [0] = earliest CTA entry,
  * [1] = earliest time its dependency wait returned, [2] = latest CTA exit.  NULL switches it off.
- * Process-global, not thread-safe: a profiling aid, not part of the product path. */
+ * The trace state belongs to the calling host thread (only its own launches are traced): a
+ * profiling aid, not part of the product path. */
 AB200_API int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches);
 
 /* ------------------------------------------------------------------------------------------
@@ -244,7 +252,8 @@ AB200_API int32_t ab200_linear_simt_bf16(const void* x, const void* w, void* out
                                int64_t ldx, int64_t ldw, int64_t ldo, void* stream);
 AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
 
-/* ---- test hooks (not on the product path) ------------------------------------------------
+/* ---- test hooks: exported ONLY by the debug flavour libarctic_b200_dbg.so (-DAB200_DEBUG), which
+ * tests/ and tools/ load; the release library has no ab200_debug_* symbol ----------------------
  * ab200_debug_cell_generic(1): route bf16 + eager-rounding emulation through the generic
  *   (instruction-heavy) cell kernel instead of the bf16x2 kernel; returns the previous setting.
  *   The two must agree bit for bit (tests/test_cell_gpu.py).
@@ -255,6 +264,7 @@ AB200_API int32_t ab200_gemm_block_n(int64_t N, int32_t sms);
  *   counts the bf16 inputs x >= lo_bound where RN(rcp(fma(ex2(x*c1), k, addend))) differs from ATen's
  *   sigmoid (mismatches[c], zero-initialised by the caller) and the lowest such input (first_bad[c],
  *   initialised to 0xffffffff).  Used once, offline, to pick constants that need no rounding guard. */
+#ifdef AB200_DEBUG
 AB200_API int32_t ab200_debug_cell_generic(int32_t on);
 AB200_API int32_t ab200_debug_sigmoid_search(const float* candidates, int32_t n_candidates,
                                              uint32_t* mismatches, uint32_t* first_bad, float lo_bound,
@@ -262,6 +272,13 @@ AB200_API int32_t ab200_debug_sigmoid_search(const float* candidates, int32_t n_
 AB200_API int32_t ab200_debug_unary_bf16(int32_t op, const uint16_t* in, uint16_t* out_fast,
                                          uint16_t* out_exact, float* out_fast32 /*optional*/,
                                          float* out_exact32 /*optional*/, int64_t n, void* stream);
+/* test hook: 1 = generic MLP-cell kernel also for bf16 + emulation (must agree bit for bit) */
+AB200_API int32_t ab200_debug_mlp_generic(int32_t on);
+/* Launch-path tunables for parameter sweeps (tools/): "pdl", "umma_m64", "gemm_2cta", "rows_per_pass",
+ * "late_trigger", "pre_stages", "l2_prefetch_kb", "gate_block_n", "head_block_n", "max_stages", ...
+ * The release library compiles the defaults in and reads no environment variable. */
+AB200_API int32_t ab200_debug_set_tunable(const char* name, int32_t value);
+#endif /* AB200_DEBUG */
 
 /* Whole draft loop: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + argmax) -> token unpack.
  * Replaces: ArcticLSTMSpeculator.generate_token_ids (arctic_speculator.py:706-751) as driven by
@@ -328,14 +345,11 @@ AB200_API int32_t ab200_sum_mlp_cell(const void* pre, int64_t pre_row_stride, co
                                      int32_t dtype, int32_t emulate_eager_rounding,
                                      uint64_t* clear_packed, uint32_t* clear_counter,
                                      void* state_q_out, float* state_scale_out, void* stream);
-/* test hook: 1 = generic kernel also for bf16 + emulation (must agree bit for bit) */
-AB200_API int32_t ab200_debug_mlp_generic(int32_t on);
-
 /* Whole draft loop of the MLP speculator: ln0 -> S x (proj GEMM -> fused cell -> head GEMM +
  * arg-max).  Replaces ArcticMLPSpeculator.generate_token_ids (arctic_speculator.py:287-326) as
  * driven by generate_proposals (:328-389), TP = 1.  Per-step weight pointers: tied checkpoints
  * repeat the same pointer (emb/head/ln: one set; proj: first + tied), untied ones list every step. */
-#define AB200_MLP_MAX_STAGES 8
+#define AB200_MLP_MAX_STAGES 16
 typedef struct ab200_mlp_speculator {
   int32_t dtype;            /* AB200_BF16 or AB200_F32 */
   int32_t emulate_eager_rounding;

@@ -13,7 +13,6 @@ Run (build container only; /root/reference does not exist on the GPU box):
 """
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -23,83 +22,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 from oracle import speculator_ref as O  # noqa: E402
 
-REF = "/root/reference"
-
-
-def load_reference_module():
-    sys.path.insert(0, REF)
-    m = types.ModuleType("vllm.model_executor.layers.sampler")
-    m.SamplerOutput = type("SamplerOutput", (), {})
-    m.get_sampler = lambda: None
-    sys.modules[m.__name__] = m
-    f8 = types.ModuleType("arctic_inference.vllm.spec_dec.fp8")
-
-    class Fp8ConfigWithEmbedding:
-        def __init__(self, *a, **k):
-            pass
-
-        def get_quant_method(self, layer, prefix=""):
-            return None
-
-        def get_name(self):
-            return "fp8"
-
-    class OriginalFp8LinearMethod:
-        def __init__(self, quant_config=None):
-            pass
-
-    f8.Fp8ConfigWithEmbedding = Fp8ConfigWithEmbedding
-    f8.OriginalFp8LinearMethod = OriginalFp8LinearMethod
-    sys.modules[f8.__name__] = f8
-    import vllm.envs as envs
-    envs.VLLM_USE_V1 = True
-    import vllm.distributed.parallel_state as ps
-
-    class G:
-        world_size = 1
-        rank = 0
-        rank_in_group = 0
-
-        def all_reduce(self, x):
-            return x
-
-        def all_gather(self, x, dim=-1):
-            return x
-
-    ps._TP = G()
-    ps._SP = G()
-    import arctic_inference.vllm.spec_dec.arctic_speculator as spec
-    return spec
-
-
-class _C:
-    pass
-
-
-def build_reference(spec, V, H, D, n_predict, max_bs, dtype, weights):
-    hf = _C()
-    hf.n_predict = n_predict
-    hf.vocab_size = V
-    hf.input_hidden_dim = H
-    hf.inner_dim = hf.emb_dim = hf.proj_dim = str(D)
-    hf.num_lookahead_tokens = n_predict
-    hf.tie_weights = hf.tie_lstm_embs = hf.scale_input = True
-    hf.method = "sum_lstm"
-    vc = _C()
-    vc.model_config = _C()
-    vc.model_config.hf_config = hf
-    vc.model_config.enforce_eager = True
-    vc.scheduler_config = _C()
-    vc.scheduler_config.max_num_seqs = max_bs
-    torch.set_default_dtype(dtype)
-    model = spec.ArcticLSTMSpeculator(vllm_config=vc)
-    model.qhead = None
-    params = dict(model.named_parameters())
-    assert set(params) == set(weights), (sorted(params), sorted(weights))
-    for k, p in params.items():
-        assert p.shape == weights[k].shape, (k, p.shape, weights[k].shape)
-        p.data.copy_(weights[k])
-    return model
+from oracle.ref_class import _C, build_reference, load_reference_module  # noqa: E402,F401  (shared with the GPU test)
 
 
 def to_np(t: torch.Tensor):

@@ -41,7 +41,7 @@ def test_unary_shortcuts_exact_on_all_65536_inputs(capi, op, name):
     exact = torch.empty_like(bits)
     f32 = torch.empty(65536, dtype=torch.float32, device=DEV)
     e32 = torch.empty_like(f32)
-    capi.check(capi.lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
+    capi.check(capi.debug_lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
                                                  f32.data_ptr(), e32.data_ptr(), 65536, st()))
     torch.cuda.synchronize()
     ref = (torch.sigmoid(x) if op == 0 else torch.nn.functional.gelu(x)).view(torch.int16)
@@ -68,7 +68,7 @@ def test_gelu_table_exact_on_all_65536_inputs(capi, op):
     bits, x = all_bf16()
     fast = torch.empty_like(bits)
     exact = torch.empty_like(bits)
-    capi.check(capi.lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
+    capi.check(capi.debug_lib().ab200_debug_unary_bf16(op, bits.data_ptr(), fast.data_ptr(), exact.data_ptr(),
                                                  None, None, 65536, st()))
     torch.cuda.synchronize()
     xin = x if op == 2 else x.flip(0)
@@ -90,7 +90,7 @@ def test_fast_paths_need_no_rounding_guard(capi, kind, lo_bound, consts):
     mism = torch.zeros(1, dtype=torch.int32, device=DEV)
     first = torch.full((1,), -1, dtype=torch.int32, device=DEV)
     n = 1 if kind == "sigmoid" else -1
-    capi.check(capi.lib().ab200_debug_sigmoid_search(cand.data_ptr(), n, mism.data_ptr(), first.data_ptr(),
+    capi.check(capi.debug_lib().ab200_debug_sigmoid_search(cand.data_ptr(), n, mism.data_ptr(), first.data_ptr(),
                                                      lo_bound, st()))
     torch.cuda.synchronize()
     assert mism.item() == 0, f"{kind}: {mism.item()} inputs misround, first {hex(first.item() & 0xFFFF)}"
@@ -100,12 +100,14 @@ def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
     B, D4 = gates.shape
     D = D4 // 4
     V = emb.shape[0]
-    lib = capi.lib()
+    # production kernel: the RELEASE library; the generic comparator lives behind a switch that only the
+    # debug flavour (libarctic_b200_dbg.so) exports
+    lib = capi.debug_lib() if generic else capi.lib()
     state = torch.empty(B, D, device=DEV, dtype=torch.bfloat16)
     cell = torch.empty_like(state)
     sq = torch.empty(B, D, device=DEV, dtype=torch.uint8) if want_fp8 else None
     ss = torch.empty(B, device=DEV, dtype=torch.float32) if want_fp8 else None
-    prev = lib.ab200_debug_cell_generic(1 if generic else 0)
+    prev = lib.ab200_debug_cell_generic(1) if generic else 0
     try:
         capi.check(lib.ab200_sum_lstm_cell(
             gates.data_ptr(), gates.stride(0), emb.data_ptr(), tok.data_ptr(), None,
@@ -115,7 +117,8 @@ def run_cell(capi, generic, gates, emb, tok, cprev, ln, alpha, want_fp8=False):
             ss.data_ptr() if want_fp8 else None, st()))
         torch.cuda.synchronize()
     finally:
-        lib.ab200_debug_cell_generic(prev)
+        if generic:
+            lib.ab200_debug_cell_generic(prev)
     return state, cell, sq, ss
 
 

@@ -161,3 +161,54 @@ def test_speculator_fp8_head_selection_and_agreement(shape):
     # and the fp8 head really is a different function (sanity: some tokens differ from the bf16 head)
     ids, hid = O.make_inputs(32, V, H, torch.bfloat16, seed=300, device=DEV)
     assert not torch.equal(m.generate_proposals(ids, hid, S), plain.generate_proposals(ids, hid, S))
+
+
+def test_default_head_selection_rule_is_the_references():
+    """arctic_speculator.py:435 hard-codes quantize_lm_head = True and :726-727 picks `qhead` iff the batch
+    the loop runs on (the PADDED batch under CUDA graphs) is <= 32.  The default-constructed class does the
+    same; `model.qhead = None` (the oracle recipe) switches to the bf16 head everywhere."""
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    V, H, D, S = 4096, 256, 256, 3
+    w = O.make_weights(V, H, D, torch.bfloat16, seed=0, device=DEV)
+    m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=64, device=DEV)
+    m.load_weights(w.items())
+    assert m.quantize_lm_head and m.qhead is not None
+    assert [m.uses_fp8_head(b) for b in (1, 25, 32, 33, 64)] == [True, True, True, False, False]
+    fp8_ref, bf16_ref = F8.RefLSTMSpeculatorFp8(w, V, S), O.RefLSTMSpeculator(w, V, S)
+    ids, hid = O.make_inputs(32, V, H, torch.bfloat16, seed=5, device=DEV)
+    got = m.generate_proposals(ids, hid, S)
+    assert (got == fp8_ref.generate_proposals(ids, hid, S)).float().mean().item() >= 0.97
+    ids40, hid40 = O.make_inputs(40, V, H, torch.bfloat16, seed=6, device=DEV)
+    agree = lambda a, b: (a == b).float().mean().item()      # GEMM accumulation order may flip a near-tie
+    assert agree(m.generate_proposals(ids40, hid40, S), bf16_ref.generate_proposals(ids40, hid40, S)) >= 0.97
+    m.qhead = None                                                   # oracle recipe
+    assert m.qhead is None and not m.uses_fp8_head(8) and not m.cuda_graphs
+    assert agree(m.generate_proposals(ids, hid, S), bf16_ref.generate_proposals(ids, hid, S)) >= 0.97
+    assert not torch.equal(m.generate_proposals(ids, hid, S), got)   # ... and it is not the FP8 function any more
+    with pytest.raises(ValueError):
+        m.qhead = object()
+    fp32 = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, device=DEV, dtype=torch.float32)
+    assert fp32.qhead is None                                        # fp32 parity mode never quantises
+
+
+def test_reload_weights_after_graph_capture():
+    """a second load_weights() must not leave captured graphs reading freed FP8
+    buffers - the head is re-quantised IN PLACE, so graphs and cached proposer plans stay valid."""
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator, ArcticProposer
+    V, H, D, S, B = 4096, 256, 256, 3, 16
+    w1 = O.make_weights(V, H, D, torch.bfloat16, seed=0, device=DEV)
+    w2 = O.make_weights(V, H, D, torch.bfloat16, seed=1, device=DEV)
+    ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=2, device=DEV)
+    m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=DEV)
+    m.load_weights(w1.items())
+    q_ptr, s_ptr = m.qhead[0].data_ptr(), m.qhead[1].data_ptr()
+    p = ArcticProposer(m)
+    first = p.propose(ids.cpu().numpy(), hid, S)                      # captures the (16, 3) graph with the FP8 head
+    m.load_weights(w2.items())
+    assert (m.qhead[0].data_ptr(), m.qhead[1].data_ptr()) == (q_ptr, s_ptr)
+    fresh = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=DEV)
+    fresh.load_weights(w2.items())
+    exp = fresh.generate_proposals(ids, hid, S)
+    assert torch.equal(m.generate_proposals(ids, hid, S), exp)
+    second = p.propose(ids.cpu().numpy(), hid, S)
+    assert (torch.from_numpy(second).to(DEV) == exp).all() and not (first == second).all()

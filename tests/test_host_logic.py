@@ -58,7 +58,7 @@ def test_speculator_constructors_validate_without_gpu():
     with pytest.raises(AssertionError):
         ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=32, n_predict=1, tie_weights=True, device="cpu")
     with pytest.raises(ValueError):
-        ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=32, n_predict=9, tie_weights=False, device="cpu")
+        ArcticMLPSpeculator(vocab_size=100, emb_dim=32, inner_dim=32, n_predict=17, tie_weights=False, device="cpu")
 
 
 def test_mlp_parameter_names_and_index_rule():

@@ -46,6 +46,10 @@ def make_model(V, H, D, n_predict, B, dtype, w, **kw):
     m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=n_predict,
                              max_num_seqs=B, dtype=dtype, device=DEV, **kw)
     m.load_weights(w.items())
+    if "quantize_lm_head" not in kw:
+        # the oracle recipe (`model.qhead = None`): bf16 head at every batch size -
+        # by default (like the reference, :435, :726-727) batches <= 32 would go through the FP8 qhead
+        m.qhead = None
     return m
 
 
@@ -91,8 +95,10 @@ def test_fused_cell_against_oracle(capi, B, D, V, dtype):
     if dtype == torch.bfloat16:
         assert relerr(state, s_ref.squeeze(1)) < BF16_STATE_TOL
         assert relerr(cell, c_ref.squeeze(1)) < BF16_STATE_TOL
-        assert (state == s_ref.squeeze(1)).float().mean().item() > 0.99   # rounding emulation
-        assert (cell == c_ref.squeeze(1)).float().mean().item() > 0.99
+        # DESIGN.md 4.1 claims BIT equality with eager PyTorch (every rounding point emulated, same gate
+        # pre-activations): assert exactly that, on the raw bits
+        assert torch.equal(state.view(torch.int16), s_ref.squeeze(1).view(torch.int16))
+        assert torch.equal(cell.view(torch.int16), c_ref.squeeze(1).view(torch.int16))
     else:
         assert relerr(state, s_ref.squeeze(1)) < FP32_STATE_TOL
         assert relerr(cell, c_ref.squeeze(1)) < FP32_STATE_TOL
@@ -177,11 +183,16 @@ def test_fused_head_argmax_matches_torch(capi, M, V, K):
     logits = F.linear(x, w)[:, :V]
     ref = torch.argmax(logits, -1)
     agree = (tok == ref).float().mean().item()
-    # a disagreement is legitimate only where our bf16 logit differs by an accumulation-order ulp
-    picked = logits.gather(1, tok.clamp(0, V - 1).unsqueeze(1)).squeeze(1)
-    best = logits.max(-1).values
-    assert ((picked.float() - best.float()).abs() <= best.float().abs() * 2 ** -7 + 1e-6).all()
-    assert agree >= (0.99 if M >= 64 else 0.0) or (tok == ref).all()
+    # A disagreement is legitimate only where bf16 rounding of two differently-ordered fp32 accumulations
+    # can change the winner: our logit and cuBLAS's may each sit one bf16 ulp away from the other's.
+    top2 = logits.float().topk(2, dim=-1).values
+    best, margin = top2[:, 0], top2[:, 0] - top2[:, 1]
+    ulp = torch.exp2(torch.floor(torch.log2(best.abs().clamp_min(1e-30))) - 7)      # bf16: 8 significand bits
+    picked = logits.gather(1, tok.clamp(0, V - 1).unsqueeze(1)).squeeze(1).float()
+    assert ((picked - best).abs() <= 2 * ulp).all()                    # never further than the rounding noise
+    decided = margin > 2 * ulp                                         # rows whose winner rounding cannot flip
+    assert torch.equal(tok[decided], ref[decided]), "token differs although the top-2 margin exceeds 2 bf16 ulps"
+    assert agree >= 0.98 or M < 16, agree
 
 
 def test_argmax_tie_break_is_lowest_index(capi):
@@ -384,6 +395,7 @@ def test_load_weights_fuses_gate_projections():
     m = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B,
                              device=DEV, enforce_eager=True)
     m.load_weights(ckpt.items())
+    m.qhead = None
     for k, p in m.named_parameters():
         assert torch.equal(p, w[k]), k
     ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=1, device=DEV)

@@ -32,7 +32,7 @@ base = cands.index((c1s[8], 1.0, 1.0))
 for lo_bound in (-16.0, -24.0, -40.0, -87.0, -3.0e38):
     mism = torch.zeros(len(cands), dtype=torch.int32, device=dev)
     first = torch.full((len(cands),), -1, dtype=torch.int32, device=dev)
-    _capi.check(_capi.lib().ab200_debug_sigmoid_search(ct.data_ptr(), len(cands), mism.data_ptr(), first.data_ptr(),
+    _capi.check(_capi.debug_lib().ab200_debug_sigmoid_search(ct.data_ptr(), len(cands), mism.data_ptr(), first.data_ptr(),
                                                        lo_bound, st), "search")
     torch.cuda.synchronize()
     m = mism.cpu().numpy()
