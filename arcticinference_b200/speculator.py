@@ -34,7 +34,7 @@ from typing import Dict, Iterable, List, Optional, Tuple
 
 import torch
 
-from . import _capi
+from . import _capi, py_custom_ops
 
 SQRT2 = 2 ** 0.5  # arctic_speculator.py:36
 
@@ -64,6 +64,9 @@ class ArcticLSTMSpeculator:
                  quantize_lm_head: Optional[bool] = None, fp8_head_max_batch: int = 32,
                  tp_size: int = 1, tp_rank: int = 0, tp_group=None) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
+        # path A goes through the additive torch ops (arctic_inference::sum_lstm_cell, ::lm_head_argmax,
+        # ::lstm_speculator_propose, ... - py_custom_ops.py), which call the C ABI
+        self._ops = py_custom_ops.load_speculator_ops()
         # Tensor parallelism of the vocab head (the reference shards ParallelLMHead over
         # max(TP, SP) ranks, vocab_parallel_embedding.py:20-35, and merges local top-1s with an
         # all_gather, arctic_speculator.py:733-744).  Everything else is replicated.
@@ -280,57 +283,32 @@ class ArcticLSTMSpeculator:
                       steps: int, states: Optional[torch.Tensor] = None,
                       cells: Optional[torch.Tensor] = None) -> None:
         ws = self._get_workspace(batch, steps)
-        with torch.cuda.device(self.device):
-            rc = self._lib.ab200_lstm_propose(
-                ctypes.byref(self._descriptor()), ids.data_ptr(), hidden.data_ptr(), hidden.stride(0),
-                batch, steps, out.data_ptr(),
-                states.data_ptr() if states is not None else None,
-                cells.data_ptr() if cells is not None else None,
-                ws.data_ptr(), ws.numel(), _capi.current_stream_ptr(self.device))
-        _capi.check(rc, "ab200_lstm_propose")
+        p = self._params
+        self._ops.lstm_speculator_propose(
+            ids[:batch], hidden[:batch], p["forget_emb.0.weight"], p["projs.0.weight"], p["projs.1.weight"],
+            p["cell_ln.0.weight"], p["cell_ln.0.bias"], p["state_ln.0.weight"], p["state_ln.0.bias"],
+            p["head.0.weight"], self._head_q, self._head_scale, self.vocab_size, steps, self.alpha, self.eps,
+            self.scale_input, int(self.emulate_eager_rounding), self.fp8_head_max_batch, ws, out, states, cells)
 
     # ---- reference method boundary ------------------------------------------------------------
     def generate_states(self, last_tokens: torch.Tensor, previous_hidden_states: torch.Tensor,
                         head_index: int, cell_states: Optional[torch.Tensor] = None
                         ) -> Tuple[torch.Tensor, torch.Tensor]:
         """arctic_speculator.py:648-691 - one step of ln0 (step 0) -> gate GEMM -> fused cell."""
-        lib, p = self._lib, self._params
+        ops, p = self._ops, self._params
         B = last_tokens.shape[0]
-        D = self.inner_dim[0]
         x = previous_hidden_states.reshape(B, -1)
-        if not x.is_contiguous():
-            x = x.contiguous()
-        code = _capi.torch_dtype_code(self.dtype)
         emu = int(self.emulate_eager_rounding)
-        stream = _capi.current_stream_ptr(self.device)
-        with torch.cuda.device(self.device):
-            if head_index == 0 and self.scale_input:                         # :656-657
-                y = torch.empty_like(x)
-                inv_sqrt2 = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(SQRT2, dtype=torch.float32))
-                _capi.check(lib.ab200_rms_scale(x.data_ptr(), y.data_ptr(), B, x.shape[1], x.stride(0),
-                                                y.stride(0), self.eps, inv_sqrt2, code, emu, stream),
-                            "ab200_rms_scale")
-                x = y
-            proj = p["projs.0.weight"] if head_index == 0 else p["projs.1.weight"]   # :659-660
-            if x.shape[1] != proj.shape[1]:
-                raise RuntimeError(f"hidden width {x.shape[1]} does not match projs weight {tuple(proj.shape)}")
-            gates = torch.empty(B, 4 * D, dtype=self.dtype, device=self.device)
-            _capi.check(lib.ab200_linear(x.data_ptr(), proj.data_ptr(), gates.data_ptr(), B, 4 * D,
-                                         x.shape[1], x.stride(0), proj.stride(0), gates.stride(0),
-                                         code, stream), "ab200_linear")
-            state = torch.empty(B, D, dtype=self.dtype, device=self.device)
-            cell = torch.empty(B, D, dtype=self.dtype, device=self.device)
-            toks = last_tokens.reshape(B).to(torch.long).contiguous()
-            cprev = None
-            if cell_states is not None:
-                cprev = cell_states.reshape(B, D).contiguous()
-            _capi.check(lib.ab200_sum_lstm_cell(
-                gates.data_ptr(), gates.stride(0), p["forget_emb.0.weight"].data_ptr(), toks.data_ptr(),
-                None, cprev.data_ptr() if cprev is not None else None,
-                p["cell_ln.0.weight"].data_ptr(), p["cell_ln.0.bias"].data_ptr(),
-                p["state_ln.0.weight"].data_ptr(), p["state_ln.0.bias"].data_ptr(),
-                state.data_ptr(), cell.data_ptr(), B, D, self.vocab_size, self.alpha, self.eps,
-                code, emu, None, None, None, None, stream), "ab200_sum_lstm_cell")
+        if head_index == 0 and self.scale_input:                         # :656-657
+            inv_sqrt2 = float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(SQRT2, dtype=torch.float32))
+            x = ops.speculator_rms_scale(x, self.eps, inv_sqrt2, emu)
+        proj = p["projs.0.weight"] if head_index == 0 else p["projs.1.weight"]   # :659-660
+        if x.shape[1] != proj.shape[1]:
+            raise RuntimeError(f"hidden width {x.shape[1]} does not match projs weight {tuple(proj.shape)}")
+        gates = ops.speculator_linear(x, proj)                           # :668
+        state, cell = ops.sum_lstm_cell(gates, p["forget_emb.0.weight"], last_tokens, cell_states,
+                                        p["cell_ln.0.weight"], p["cell_ln.0.bias"], p["state_ln.0.weight"],
+                                        p["state_ln.0.bias"], self.alpha, self.eps, emu)   # :667-689
         return state.unsqueeze(1), cell.unsqueeze(1)
 
     def greedy_tokens(self, states: torch.Tensor) -> torch.Tensor:
@@ -343,25 +321,7 @@ class ArcticLSTMSpeculator:
                 _capi.check(self._lib.ab200_argmax_unpack(keys.data_ptr(), toks.data_ptr(), states.shape[0], 1,
                                                           _capi.current_stream_ptr(self.device)), "ab200_argmax_unpack")
             return toks
-        lib, head = self._lib, self._params["head.0.weight"]
-        B, D = states.shape
-        states = states.contiguous()
-        packed = torch.zeros(B + 1, dtype=torch.int64, device=self.device)   # [B] slots + done counter
-        out = torch.empty(B, dtype=torch.long, device=self.device)
-        code = _capi.torch_dtype_code(self.dtype)
-        ws = None
-        if self.dtype == torch.float32:
-            ws = torch.empty(B * self.vocab_size, dtype=torch.float32, device=self.device)
-        stream = _capi.current_stream_ptr(self.device)
-        with torch.cuda.device(self.device):
-            _capi.check(lib.ab200_head_argmax(states.data_ptr(), head.data_ptr(), B, head.shape[0], D,
-                                              self.vocab_size, states.stride(0), head.stride(0),
-                                              packed.data_ptr(), out.data_ptr(), 1,
-                                              packed[B:].data_ptr(), code,
-                                              ws.data_ptr() if ws is not None else None,
-                                              ws.numel() * 4 if ws is not None else 0, stream),
-                        "ab200_head_argmax")
-        return out
+        return self._ops.lm_head_argmax(states, self._params["head.0.weight"], self.vocab_size)
 
     # ---- tensor-parallel head -----------------------------------------------------------------
     def local_argmax_keys(self, states: torch.Tensor) -> torch.Tensor:
@@ -419,7 +379,12 @@ class ArcticLSTMSpeculator:
             states, cell_states = self.generate_states(last_tokens, previous_hidden_states,
                                                        head_index, cell_states)
             previous_hidden_states = states
-            last_tokens = self.greedy_tokens(states.flatten(0, 1)).reshape(batch_size, -1)
+            if self._head_q is not None and batch_size <= self.fp8_head_max_batch and self.tp_size == 1:
+                # :726-727 - the FP8 qhead for batch <= 32 (same rule as inside the fused loop)
+                last_tokens = self._ops.lm_head_argmax_fp8(states.flatten(0, 1), self._head_q, self._head_scale,
+                                                           self.vocab_size).reshape(batch_size, -1)
+            else:
+                last_tokens = self.greedy_tokens(states.flatten(0, 1)).reshape(batch_size, -1)
             if next_tokens_tensors[head_index] is None:
                 next_tokens_tensors[head_index] = last_tokens
             else:

@@ -152,3 +152,18 @@ def test_host_helpers():
     from arcticinference_b200.speculator import padding_size, pad_vocab_size
     assert [padding_size(n) for n in (1, 5, 9, 33, 64, 65, 257)] == [1, 6, 12, 48, 64, 96, 384]
     assert pad_vocab_size(128256) == 128256 and pad_vocab_size(1000) == 1024
+
+
+def test_speculator_ops_registered_cuda_only(built_lib):
+    """additive path-A ops in the arctic_inference namespace (the reference has none, F1)."""
+    from arcticinference_b200 import py_custom_ops
+    ns = py_custom_ops.load_speculator_ops()
+    for name in ("speculator_rms_scale", "speculator_linear", "linear_bf16", "sum_lstm_cell", "lm_head_argmax",
+                 "lm_head_argmax_fp8", "lstm_speculator_propose"):
+        schema = str(getattr(ns, name).default._schema)
+        assert schema.startswith(f"arctic_inference::{name}("), schema
+    assert "Tensor(a!) workspace, Tensor(b!) tokens_out" in str(ns.lstm_speculator_propose.default._schema)
+    with pytest.raises(NotImplementedError):                  # CUDA key only: CPU tensors are not silently handled
+        ns.lm_head_argmax(torch.zeros(2, 8), torch.zeros(16, 8), 16)
+    meta = torch.empty(3, 1, 8, device="meta", dtype=torch.bfloat16)
+    assert ns.speculator_linear(meta, torch.empty(32, 8, device="meta", dtype=torch.bfloat16)).shape == (3, 1, 32)
