@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libarctic_b200.so")
 LIB_DEBUG = os.path.join(HERE, "libarctic_b200_dbg.so")
-SOURCES = ["kv_write.cu", "lstm_cell.cu", "mlp_cell.cu", "gemm_sm100.cu", "quant_fp8.cu", "speculator.cu"]
+SOURCES = ["kv_write.cu", "kv_rope_write.cu", "lstm_cell.cu", "mlp_cell.cu", "gemm_sm100.cu", "quant_fp8.cu", "speculator.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -13,6 +13,7 @@ DEBUG_LIB_PATH = os.path.join(HERE, "libarctic_b200_dbg.so")
 
 AB200_F32, AB200_F16, AB200_BF16 = 0, 1, 2
 AB200_KV_AUTO, AB200_KV_FP8_E4M3, AB200_KV_FP8_E5M2 = 0, 1, 2
+AB200_ROPE_FP32, AB200_ROPE_STORAGE = 0, 1
 AB200_E_INVALID, AB200_E_UNSUPPORTED, AB200_E_CUDA, AB200_E_WORKSPACE = -1, -2, -3, -4
 
 
@@ -59,6 +60,11 @@ SIGNATURES = {
                                       POINTER(c_void_p), POINTER(c_void_p), c_int32,
                                       c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
                                       c_int32, c_int32, c_void_p]),
+    "ab200_kv_rope_write_bulk": (c_int32, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                           c_int32, c_int32, c_int32, POINTER(c_void_p), POINTER(c_void_p),
+                                           POINTER(c_void_p), POINTER(c_void_p), c_int32, c_void_p, c_int64,
+                                           c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                           c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "ab200_rms_scale": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                   c_float, c_float, c_int32, c_int32, c_void_p]),
     "ab200_sum_lstm_cell": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,

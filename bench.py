@@ -406,6 +406,10 @@ def bench_kv_write(dev, iters: int, peak_gbs: float):
     out["fp8_cache"] = {"value": alg8 / ms8 / 1e6, "unit": "GB/s", "ms": ms8, "algorithmic_bytes": alg8,
                         "frac_of_hbm_peak": alg8 / ms8 / 1e6 / peak_gbs}
     del kv8, kc8, vc8
+    try:
+        out["rope_fused"] = bench_rope_fused(dev, peak_gbs, kc, vc, slots, sc)
+    except Exception as e:  # noqa: BLE001
+        out["rope_fused"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     # end to end with HOST buffers: pinned K/V rows + slot map copied in, inside the timed region
     hk, hv, hs = keys.cpu().pin_memory(), vals.cpu().pin_memory(), slots.cpu().pin_memory()
     dk, dv, ds = torch.empty_like(keys), torch.empty_like(vals), torch.empty_like(slots)
@@ -421,6 +425,69 @@ def bench_kv_write(dev, iters: int, peak_gbs: float):
                   "d2h_bytes_per_step": 0, "note": "PCIe-bound: the K/V rows are produced on the device in "
                   "the real caller (llama_swiftkv.py:263-274)"}
     return out
+
+
+def bench_rope_fused(dev, peak_gbs, kc, vc, slots, sc, iters: int = 10):
+    """K-rotary + cache scatter straight from the per-layer kv_proj outputs (cfg2 geometry), against
+    the reference flow on the same GPU: per layer rotary_emb (vLLM's CUDA op) on k, cat -> [T, L*n] x 2, bulk write
+    (llama_swiftkv.py:263-274, 599-628) - with OUR bulk kernel as its last step, i.e. its best case."""
+    import torch
+    from arcticinference_b200 import py_custom_ops, swiftkv
+    from oracle import kv_rope_ref as R
+    L, T, Hkv, Dh, bs = (KV_CFG[k] for k in ("L", "T", "Hkv", "Dh", "bs"))
+    n = Hkv * Dh
+    g = torch.Generator(device=dev).manual_seed(1)
+    kv_list = [torch.randn(T, 2 * n, device=dev, dtype=torch.bfloat16, generator=g) for _ in range(L)]
+    positions = torch.randint(0, 8192, (T,), device=dev, generator=g, dtype=torch.int64)
+    cos_sin = R.make_cos_sin_cache(8192, Dh, torch.bfloat16, device=dev)
+    fused = lambda: swiftkv.kv_rope_write_bulk(kv_list, positions, cos_sin, kc, vc, slots, "auto", sc, sc, Hkv, Dh)
+    rot_kind = "torch formula (vLLM forward_native)"
+    rotary = None
+    try:
+        import vllm._custom_ops as vops
+        qdummy = torch.empty(T, n, device=dev, dtype=torch.bfloat16)
+        vops.rotary_embedding(positions, qdummy, kv_list[0][:, :n].clone(), Dh, cos_sin, True)
+        rotary = lambda k: (vops.rotary_embedding(positions, qdummy, k, Dh, cos_sin, True), k)[1]
+        rot_kind = "vLLM rotary_embedding CUDA op (in place)"
+    except Exception:  # noqa: BLE001
+        rotary = lambda k: R.rope_torch(positions, k, cos_sin, Dh, Dh, True)
+
+    def reference_flow():
+        ks, vs = [], []
+        for kv in kv_list:
+            k, v = kv.chunk(2, dim=-1)
+            ks.append(rotary(k))        # in place on the kv_proj output like the reference (:270)
+            vs.append(v)
+        py_custom_ops.reshape_and_cache_flash_bulk(torch.cat(ks, -1), torch.cat(vs, -1), kc, vc, slots, "auto", sc, sc,
+                                                   Hkv, Dh)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(3):
+            torch.cuda._sleep(SPIN_CYCLES)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) / iters)
+        return statistics.median(ts)
+
+    ms = timed(fused)
+    ref_ms = timed(reference_flow)
+    alg = T * L * 2 * n * (2 + 2) + 16 * T
+    return {"workload": "K-rotary + paged-cache scatter of 16 layers x 8192 tokens straight from the kv_proj outputs "
+                        "(no [T, L*n] staging), bf16, NeoX rotary, head 128",
+            "ms": ms, "value": alg / ms / 1e6, "unit": "GB/s", "algorithmic_bytes": alg,
+            "frac_of_hbm_peak": alg / ms / 1e6 / peak_gbs, "frac_of_8TBs_nominal": alg / ms / 1e6 / 8000.0,
+            "reference_flow_ms": ref_ms, "reference_flow": f"per layer {rot_kind} + 2 x torch.cat + our bulk write",
+            "speedup_vs_reference_flow": ref_ms / ms,
+            "reference_flow_bytes": T * L * n * 2 * 10, "note": "the reference flow moves 10 T*L*n*e bytes after the "
+            "projection GEMM (rotary r+w, cat r+w of k and v, bulk r+w), the fused kernel 4"}
 
 
 def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096, V: int = 128256, iters: int = 10,

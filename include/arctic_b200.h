@@ -96,6 +96,43 @@ AB200_API int32_t ab200_kv_write_bulk(const void* keys, const void* values,
                             int32_t num_heads, int32_t head_size,
                             int32_t src_dtype, int32_t kv_dtype, void* stream);
 
+/* SwiftKV: K-rotary + paged-cache scatter for all SwiftKV layers in ONE launch, straight from the per-layer
+ * kv_proj outputs - no [T, L*n] k_states / v_states staging tensors.
+ * Replaces, per forward pass: the loop arctic_inference/vllm/swiftkv/llama_swiftkv.py:263-274
+ *   (kv = kv_proj_swiftkv(h); k, v = kv.chunk(2, -1); _, k = rotary_emb(positions, q, k); cat),
+ *   the bulk cache write :599-628 (reshape_and_cache_flash_bulk) and, optionally, the
+ *   index_select of k_states / v_states for the surviving tokens :669-685.
+ *   kv_ptrs        HOST array of num_layers device pointers: layer l's kv_proj output [T, >= v_offset + n],
+ *                  row stride kv_row_stride; K in columns [0, n), V in columns [v_offset, v_offset + n)
+ *                  (kv.chunk(2, dim=-1): v_offset = n).  n = num_heads * head_size.
+ *   positions      [T] int64;  cos_sin_cache [max_position, >= rot_dim] in the kv dtype, row = cos (rot_dim/2)
+ *                  | sin (rot_dim/2) - vLLM's RotaryEmbedding.cos_sin_cache;  is_neox: 1 = pairs (i, i + rot_dim/2),
+ *                  0 = GPT-J pairs (2i, 2i+1);  only the first rot_dim elements of every head are rotated.
+ *   rope_rounding  AB200_ROPE_FP32 (default contract): x' = R(x*cos - y*sin), y' = R(y*cos + x*sin) with fp32
+ *                  arithmetic and ONE rounding to the storage dtype - bit-identical to vLLM's rotary_embedding CUDA
+ *                  op (the op the reference reaches through rotary_emb; pinned against the installed wheel's op on
+ *                  a B200).  AB200_ROPE_STORAGE: one rounding after every operation, R(R(x*cos) - R(y*sin)) =
+ *                  vLLM's forward_native / apply_rotary_emb_torch in the storage dtype (differs by the rounding
+ *                  of the two products, usually one storage ulp).  Either way the cache is bit-identical to the corresponding reference sequence; V is a
+ *                  bit copy (tests/test_kv_rope_gpu.py).
+ *   caches, slot_mapping, block_stride, block_size, kv_dtype, scales: as ab200_kv_write_bulk.
+ *   sel_indices    (optional, device [num_sel] int64, negative wraps): the rotated K rows and V rows of these
+ *                  tokens are also written compactly to k_states_out / v_states_out [num_sel, num_layers*n]
+ *                  (what swiftkv_select hands to the decode runner), by extra CTAs of the same launch.
+ * Requires bf16 / f16, head_size a power of two in [8, 256], rot_dim a power of two in [16, head_size]. */
+enum ab200_rope_rounding { AB200_ROPE_FP32 = 0, AB200_ROPE_STORAGE = 1 };
+AB200_API int32_t ab200_kv_rope_write_bulk(const void* const* kv_ptrs, int64_t kv_row_stride, int64_t v_offset,
+                                           const int64_t* positions, const void* cos_sin_cache,
+                                           int64_t cos_sin_row_stride, int64_t max_position, int32_t rot_dim,
+                                           int32_t is_neox, int32_t rope_rounding, void* const* key_cache_ptrs,
+                                           void* const* value_cache_ptrs, const float* const* k_scale_ptrs,
+                                           const float* const* v_scale_ptrs, int32_t num_layers,
+                                           const int64_t* slot_mapping, int64_t num_tokens, int64_t block_stride,
+                                           int32_t block_size, int32_t num_heads, int32_t head_size,
+                                           int32_t src_dtype, int32_t kv_dtype, const int64_t* sel_indices,
+                                           int64_t num_sel, void* k_states_out, void* v_states_out,
+                                           int64_t states_row_stride, void* stream);
+
 /* SwiftKV select: dst_i[j, :] = src_i[indices[j], :] for up to 8 tensors in
  * ONE launch.  Replaces the five torch.index_select calls of LlamaSwiftKVModel.swiftkv_select
  * (arctic_inference/vllm/swiftkv/llama_swiftkv.py:669-685) that compact hidden_states, residual,
