@@ -66,7 +66,8 @@ struct Tune {
   int head_block_n = 0;    // debug: force the tile width of the arg-max GEMM
   int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)
   int early_producer = 1;  // TMA producer starts streaming W before TMEM allocation completes
-  int dyn_tiles = 0;       // debug: reserved
+  int gate_kbs = 2;        // k-blocks per TMA request / pipeline stage of the store-epilogue GEMM (1 or 2)
+  int head_kbs = 2;        // ... of the arg-max (vocab head) GEMM (applies to <= 64 rows only)
 };
 #ifdef AB200_DEBUG
 Tune& tune_mut();
@@ -84,8 +85,8 @@ inline const Tune& tune() {
 // kernel produced; both are no-ops for launches without the attribute.
 inline bool pdl_enabled() { return tune().pdl != 0; }
 
-// Optional device-side timeline (ab200_set_trace_buffer): every traced launch owns 4 u64 slots
-// {min CTA entry, min time after the PDL wait, max CTA exit, unused} of %globaltimer nanoseconds.
+// Optional device-side timeline (ab200_set_trace_buffer): every traced launch owns kTraceWords u64 words
+// of %globaltimer nanoseconds (see trace_stamp).
 // next_trace_slot() returns nullptr when tracing is off.  The trace state is per host thread.
 unsigned long long* next_trace_slot();
 
@@ -221,11 +222,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// which: 0 = CTA entry (min), 1 = dependency resolved (min), 2 = CTA exit (max)
+// Trace words per launch: 0 = first CTA entry (min), 1 = dependency resolved (min), 2 = last CTA exit (max),
+// 3 = first operand bytes landed (min), 4 = last operand bytes landed (max), 5 = first CTA exit (min).
+// Words 3..5 are written by the GEMM kernels only.
+constexpr int kTraceWords = 8;
 __device__ __forceinline__ void trace_stamp(unsigned long long* slot, int which) {
   if (slot != nullptr) {
     const unsigned long long t = globaltimer_ns();
-    if (which == 2) atomicMax(slot + 2, t);
+    if (which == 2 || which == 4) atomicMax(slot + which, t);
     else atomicMin(slot + which, t);
   }
 }

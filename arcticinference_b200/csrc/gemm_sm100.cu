@@ -82,6 +82,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// 3-D box {128 bytes of K, rows, k-blocks}: ONE request brings several k-blocks, each landing as its own
+// [rows x 128 B] SWIZZLE_128B slab (the k-block index is the outermost box dimension)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
+                                            int32_t c1, int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
                    reinterpret_cast<uint64_t>(desc)),
@@ -184,6 +194,8 @@ struct GemmParams {
   int32_t pre_stages;      // smem stages filled with W before the dependency wait
   int32_t late_trigger;    // 1: griddepcontrol.launch_dependents after the last TMA load
   int32_t m64;             // 1: UMMA M = 64 (MT == 1, <= 64 rows): row r lives in TMEM lane (r/16)*32 + r%16
+  int32_t kbs;             // k-blocks per pipeline stage = per TMA request (1: 2-D maps; 2: 3-D maps, MT == 1)
+  uint32_t a_pitch;        // kbs == 2: bytes between the k-block slabs of the activation box (box rows * 128)
   uint32_t tx_bytes;    // bytes landing per stage
   uint32_t idesc;
   __nv_bfloat16* out;   // EPI_STORE
@@ -224,7 +236,7 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u * (MT == 1 ? static_cast<uint32_t>(p.kbs) : 1u);
   const uint32_t stage_bytes = kASlot + b_bytes;
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -234,22 +246,33 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
   const uint32_t flag_slot = tmem_slot + 8u;
 
-  const int num_kb = p.num_k_blocks;
+  const int num_kb = p.num_k_blocks;   // pipeline steps per tile (each of kbs k-blocks)
   const int my_tiles = static_cast<int>(blockIdx.x) < p.num_n_tiles
                            ? (p.num_n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                            : 0;
   // producer's view: linearised (tile, k-block) sequence of this CTA
   const int total = my_tiles * num_kb;
+  // kbs == 2: a stage holds TWO k-blocks fetched by ONE request per operand (3-D tensor map).  The per-SM rate
+  // of TMA requests, not HBM, bounded the narrow-tile GEMM (time per k-block ~0.3 us whatever the box size,
+  // profiles/r2_gemm_tune.md): half the requests and half the barrier round trips for the same bytes in flight.
+  // A k-block index beyond K/64 (odd block counts) is out of bounds for the map and arrives as zeros.
+  const int kbs = MT == 1 ? p.kbs : 1;
+  const uint32_t b_pitch = b_bytes / kbs;     // bytes of one k-block slab of W
   auto n0_of = [&](int g) { return (static_cast<int>(blockIdx.x) + (g / num_kb) * static_cast<int>(gridDim.x)) * p.block_n; };
   auto load_x = [&](int g, int stage) {
     const uint32_t sa = smem_base + stage * stage_bytes;
+    if (kbs == 2) {
+      tma_load_3d(sa, &tmap_x, full_bar(stage), 0, 0, 2 * (g % num_kb), kEvictLast);
+    } else {
 #pragma unroll
-    for (int t = 0; t < MT; ++t)
-      tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
+      for (int t = 0; t < MT; ++t)
+        tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
+    }
   };
   auto load_w = [&](int g, int stage) {
     const uint32_t sa = smem_base + stage * stage_bytes;
-    tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
+    if (kbs == 2) tma_load_3d(sa + kASlot, &tmap_w, full_bar(stage), 0, n0_of(g), 2 * (g % num_kb), kEvictFirst);
+    else tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
   };
   const int pre = total < p.pre_stages ? total : p.pre_stages;
 
@@ -271,7 +294,8 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       load_w(g, g);
     }
     const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
-    for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
+    if (kbs == 1)
+      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -327,17 +351,33 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
         tc_fence_after();
+        if (p.trace != nullptr && lane == 0) {
+          if (it == 0 && kb == 0) trace_stamp(p.trace, 3);
+          if (it == my_tiles - 1 && kb == num_kb - 1) trace_stamp(p.trace, 4);
+        }
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t db = smem_desc_sw128(sa + kASlot);
+          if (MT == 1 && p.kbs == 2) {
+            const uint32_t tmem_d = tmem_base + acc * kAccSlot;
 #pragma unroll
-          for (int t = 0; t < MT; ++t) {
-            const uint64_t da = smem_desc_sw128(sa + t * kABytes);
-            const uint32_t tmem_d = tmem_base + (acc * MT + t) * kAccSlot;
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t da = smem_desc_sw128(sa + kk * p.a_pitch);
+              const uint64_t db = smem_desc_sw128(sa + kASlot + kk * (b_bytes >> 1));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // one MMA consumes 32 B of the 128 B swizzle row: +2 in the (>>4) address field
-              umma<KIND>(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma<KIND>(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | kk | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            const uint64_t db = smem_desc_sw128(sa + kASlot);
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+              const uint64_t da = smem_desc_sw128(sa + t * kABytes);
+              const uint32_t tmem_d = tmem_base + (acc * MT + t) * kAccSlot;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // one MMA consumes 32 B of the 128 B swizzle row: +2 in the (>>4) address field
+                umma<KIND>(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(empty_bar(stage));                      // smem stage reusable once MMAs retire
@@ -473,7 +513,10 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (threadIdx.x == 0) trace_stamp(p.trace, 2);
+  if (threadIdx.x == 0) {
+    trace_stamp(p.trace, 2);
+    trace_stamp(p.trace, 5);
+  }
 }
 
 
@@ -787,6 +830,28 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K
   return AB200_OK;
 }
 
+// 3-D view of the same matrix for multi-k-block requests: dims {128 bytes of K, rows, K / k_elems}, box
+// {k_elems, box_rows, kbs}; needs K % k_elems == 0 (a partial k-block would run into the next row)
+static int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                      int esize, int kbs) {
+  EncodeTiledFn enc = get_encode_fn();
+  AB200_REQUIRE(enc != nullptr, AB200_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const int k_elems = kRowBytes / esize;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(k_elems), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(K / k_elems)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld) * esize, static_cast<cuuint64_t>(kRowBytes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(k_elems), static_cast<cuuint32_t>(box_rows),
+                       static_cast<cuuint32_t>(kbs)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AB200_REQUIRE(r == CUDA_SUCCESS, AB200_E_CUDA,
+                "cuTensorMapEncodeTiled(3d) failed (%d) rows=%lld K=%lld ld=%lld box_rows=%d", (int)r,
+                (long long)rows, (long long)K, (long long)ld, box_rows);
+  return AB200_OK;
+}
+
 static int sm_count() { return device_sm_count(); }
 
 // Tensor maps depend only on (base, rows, K, ld, box rows, element size), never on the contents, so a
@@ -795,9 +860,10 @@ static int sm_count() { return device_sm_count(); }
 struct TmapKey {
   const void* base;
   int64_t rows, K, ld;
-  int32_t box_rows, esize;
+  int32_t box_rows, esize, kbs;
   bool operator==(const TmapKey& o) const {
-    return base == o.base && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows && esize == o.esize;
+    return base == o.base && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows &&
+           esize == o.esize && kbs == o.kbs;
   }
 };
 struct TmapCache {
@@ -807,15 +873,16 @@ struct TmapCache {
   int used = 0, next = 0;
 };
 static int get_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
-                    int esize) {
+                    int esize, int kbs = 1) {
   static thread_local TmapCache cache;
-  const TmapKey key{base, rows, K, ld, box_rows, esize};
+  const TmapKey key{base, rows, K, ld, box_rows, esize, kbs};
   for (int i = 0; i < cache.used; ++i)
     if (cache.keys[i] == key) {
       *map = cache.maps[i];
       return AB200_OK;
     }
-  int rc = make_tmap(map, base, rows, K, ld, box_rows, esize);
+  int rc = kbs == 1 ? make_tmap(map, base, rows, K, ld, box_rows, esize)
+                    : make_tmap3(map, base, rows, K, ld, box_rows, esize, kbs);
   if (rc != AB200_OK) return rc;
   const int slot = cache.used < TmapCache::kEntries ? cache.used++ : (cache.next++ % TmapCache::kEntries);
   cache.keys[slot] = key;
@@ -860,7 +927,10 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   const int sms = sm_count();
   int bn = pick_block_n(n_valid, sms, kMaxBlockN / MT);
   const int forced_bn = EPI == EPI_STORE ? tune().gate_block_n : tune().head_block_n;
-  if (forced_bn >= 16 && forced_bn <= kMaxBlockN / MT && forced_bn % 16 == 0) bn = forced_bn;   // debug sweeps only
+  // debug sweeps only (UMMA N must be a multiple of 16 for M = 128, of 8 for M = 64)
+  if (forced_bn >= 16 && forced_bn <= kMaxBlockN / MT &&
+      forced_bn % ((MT == 1 && m_rows <= 64 && tune().umma_m64) ? 8 : 16) == 0)
+    bn = forced_bn;
   const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
   const int box_m = MT == 1 ? static_cast<int>((m_rows + 7) / 8 * 8) : kTileM;
   // weight bytes in flight per SM = stages x tile: with a 7-stage ring the 8B gate GEMM was bound by
@@ -868,19 +938,28 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   // therefore sized to the rows the batch really has
   // (the MMA reads all M rows of the slot, valid or not: M = 64 -> 8 KiB, M = 128 -> 16 KiB)
   const bool m64 = MT == 1 && m_rows <= 64 && tune().umma_m64;
-  const uint32_t a_slot = m64 ? 64u * 128u : MT * kABytes;
-  const uint32_t stage_bytes = a_slot + bn * 128;
+  constexpr int esize = KIND == KIND_BF16 ? 2 : 1;
+  constexpr int k_elems = kRowBytes / esize;
+  // Two k-blocks per TMA request (3-D maps): the per-SM rate of TMA requests, not HBM, bounded the GEMMs with
+  // narrow tiles - time per k-block was ~0.3 us whatever the box size (profiles/r2_gemm_tune.md).  Always for
+  // the store-epilogue (gate / proj) GEMM: 8B gate 5.9 -> 6.1 TB/s while streaming, GPT-OSS gate (K = 2880) 4.6 ->
+  // 6.3 TB/s; for the vocab head only with the 8 KiB activation slab (<= 64 rows: 3 stages of 60 KB beat 7 of
+  // 30 KB, 6.17 -> 6.30 TB/s) - with 16 KiB slabs only 2 stages would fit and it loses.
+  int kbs = 1;
+  const int want = EPI == EPI_STORE ? tune().gate_kbs : (m64 ? tune().head_kbs : 1);
+  if (MT == 1 && want == 2 && K % k_elems == 0 && K >= 2 * k_elems) kbs = 2;
+  const uint32_t a_slab = m64 ? 64u * 128u : MT * kABytes;      // one k-block of activations (rows the MMA reads)
+  const uint32_t a_slot = a_slab * kbs;
+  const uint32_t stage_bytes = a_slot + bn * 128 * kbs;
   int stages = (kSmemLimit - 1024 /*align slack*/ - 256 /*barriers*/) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (tune().max_stages >= 2 && stages > tune().max_stages) stages = tune().max_stages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
 
-  constexpr int esize = KIND == KIND_BF16 ? 2 : 1;
-  constexpr int k_elems = kRowBytes / esize;
   CUtensorMap tmx, tmw;
-  rc = get_tmap(&tmx, x, m_rows, K, ldx, box_m, esize);
+  rc = get_tmap(&tmx, x, m_rows, K, ldx, box_m, esize, kbs);
   if (rc != AB200_OK) return rc;
-  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn, esize);
+  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn, esize, kbs);
   if (rc != AB200_OK) return rc;
 
   GemmParams p;
@@ -888,14 +967,16 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.n_valid = static_cast<int32_t>(n_valid);
   p.block_n = bn;
   p.num_n_tiles = num_n_tiles;
-  p.num_k_blocks = static_cast<int32_t>((K + k_elems - 1) / k_elems);
+  p.num_k_blocks = static_cast<int32_t>(((K + k_elems - 1) / k_elems + kbs - 1) / kbs);   // pipeline steps per tile
+  p.kbs = kbs;
+  p.a_pitch = static_cast<uint32_t>(box_m) * 128u;
   p.stages = stages;
   p.l2_prefetch_kb = pdl_enabled() ? tune().l2_prefetch_kb : 0;
   p.late_trigger = gemm_late_trigger();
   p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
   if (p.pre_stages < 0) p.pre_stages = 0;
-  p.tx_bytes = static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u;
+  p.tx_bytes = (static_cast<uint32_t>(MT * box_m) * 128u + static_cast<uint32_t>(bn) * 128u) * kbs;
   // instruction descriptor: D=f32 [4,6), A/B format [7,10)/[10,13) (kind::f16: 1 = bf16;
   // kind::f8f6f4: 0 = e4m3), K-major A/B, N>>3 [17,23), M>>4 [24,29)
   const uint32_t fmt = KIND == KIND_BF16 ? 1u : 0u;
@@ -965,6 +1046,8 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
   p.m64 = 0;
+  p.kbs = 1;
+  p.a_pitch = 0;
   p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u);   // both CTAs
   // instruction descriptor: D = f32, A/B = bf16, K-major, N >> 3, M = 256 >> 4
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (16u << 24);

@@ -27,7 +27,7 @@ static thread_local unsigned long long* g_trace_base = nullptr;
 static thread_local int g_trace_cap = 0, g_trace_next = 0;
 unsigned long long* next_trace_slot() {
   if (g_trace_base == nullptr || g_trace_next >= g_trace_cap) return nullptr;
-  return g_trace_base + 4 * static_cast<size_t>(g_trace_next++);
+  return g_trace_base + kTraceWords * static_cast<size_t>(g_trace_next++);
 }
 #ifdef AB200_DEBUG
 Tune& tune_mut() {
@@ -141,7 +141,7 @@ extern "C" int32_t ab200_debug_set_tunable(const char* name, int32_t value) {
       {"rows_per_pass", &t.rows_per_pass}, {"late_trigger", &t.late_trigger},
       {"pre_stages", &t.pre_stages}, {"l2_prefetch_kb", &t.l2_prefetch_kb},
       {"gate_block_n", &t.gate_block_n}, {"head_block_n", &t.head_block_n},
-      {"max_stages", &t.max_stages}, {"early_producer", &t.early_producer}, {"dyn_tiles", &t.dyn_tiles}};
+      {"max_stages", &t.max_stages}, {"early_producer", &t.early_producer}, {"gate_kbs", &t.gate_kbs}, {"head_kbs", &t.head_kbs}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) {
       *e.p = value;

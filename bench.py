@@ -302,11 +302,11 @@ def device_timeline(model, ids, hid, B: int, S: int, replays: int = 7):
     lib = _capi.lib()
     dev = ids.device
     n_slots = 3 * S + 3
-    trace = torch.empty(n_slots, 4, dtype=torch.int64, device=dev)
+    trace = torch.empty(n_slots, 8, dtype=torch.int64, device=dev)      # AB200_TRACE_WORDS
 
     def reset():
-        trace[:, :2] = torch.iinfo(torch.int64).max
-        trace[:, 2:] = 0
+        trace.zero_()
+        trace[:, [0, 1, 3, 5]] = torch.iinfo(torch.int64).max            # the "min" words
 
     reset()
     model._get_workspace(B, S)
@@ -346,7 +346,9 @@ def device_timeline(model, ids, hid, B: int, S: int, replays: int = 7):
     med = np.median(np.stack(runs), 0)
     t0 = stamps[0, 0]
     return {"names": names, "run_us": [float(v) for v in med], "replay_us": float(np.median(ev_us)),
-            "last": [[float((stamps[i, j] - t0) / 1e3) for j in range(3)] for i in range(len(names))]}
+            # entry, dep_ok, exit, first_data, last_data, first_exit (the last three: GEMM kernels only, else None)
+            "last": [[(float((stamps[i, j] - t0) / 1e3) if 0 < stamps[i, j] < 2 ** 62 else None) for j in range(6)]
+                     for i in range(len(names))]}
 
 
 def bench_kv_write(dev, iters: int, peak_gbs: float):
@@ -1014,7 +1016,8 @@ def run_ours(args):
         "head_argmax_frac_of_hbm_peak" if not dual else "dual_frac_of_hbm_peak": big_bytes / big_us / 1e3 / peak,
         "share_of_replay": {k: sum(v for n, v in zip(tl["names"], tl["run_us"]) if n.rstrip("0123456789") == k)
                             / tl["replay_us"] for k in groups},
-        "timeline_us": {n: {"entry": e, "dep_ok": d, "exit": x} for n, (e, d, x) in zip(tl["names"], tl["last"])},
+        "timeline_us": {n: dict(zip(("entry", "dep_ok", "exit", "first_data", "last_data", "first_exit"), row))
+                        for n, row in zip(tl["names"], tl["last"])},
     }
     line = {
         "metric": METRIC, "value": total_units / max_ms * 1e3, "unit": UNIT, "n_gpus": world,

@@ -53,12 +53,15 @@ AB200_API int64_t ab200_launch_count(void);
  * once per device before capturing graphs (the host classes do, at construction). */
 AB200_API int32_t ab200_init(void* stream);
 
-/* Device-side timeline for profiling a (graph-captured) draft loop.  device_slots: 4 uint64 per
- * traced launch, initialised by the caller to {~0, ~0, 0, 0}; each speculator kernel launched while
- * tracing is on takes the next slot and records %globaltimer ns: [0] = earliest CTA entry,
- * [1] = earliest time its dependency wait returned, [2] = latest CTA exit.  NULL switches it off.
+/* Device-side timeline for profiling a (graph-captured) draft loop.  device_slots: AB200_TRACE_WORDS (8)
+ * uint64 per traced launch, initialised by the caller to ~0 in the "min" words {0, 1, 3, 5} and 0 elsewhere; each
+ * speculator kernel launched while tracing is on takes the next slot and records %globaltimer ns: [0] = earliest
+ * CTA entry, [1] = earliest time its dependency wait returned, [2] = latest CTA exit, and (GEMM kernels)
+ * [3] = first operand bytes landed in shared memory, [4] = last operand bytes landed, [5] = earliest CTA exit.
+ * NULL switches it off.
  * The trace state belongs to the calling host thread (only its own launches are traced): a
  * profiling aid, not part of the product path. */
+#define AB200_TRACE_WORDS 8
 AB200_API int32_t ab200_set_trace_buffer(uint64_t* device_slots, int32_t max_launches);
 
 /* ------------------------------------------------------------------------------------------

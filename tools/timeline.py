@@ -15,7 +15,9 @@ hid = torch.randn(B, H, generator=g).to(torch.bfloat16).to(dev)
 tl = bench.device_timeline(model, ids, hid, B, S)
 print("median run(dep->exit) over 7 replays:", " ".join(f"{n}={v:.1f}" for n, v in zip(tl["names"], tl["run_us"])))
 print(f"graph replay {tl['replay_us']:.1f} us (events); timeline in us relative to first CTA entry")
-print(f"{'kernel':8s} {'entry':>8s} {'dep-ok':>8s} {'exit':>8s} | {'run(dep->exit)':>14s} {'early-start':>11s}")
-for n, (en, dp, ex) in zip(tl["names"], tl["last"]):
-    print(f"{n:8s} {en:8.1f} {dp:8.1f} {ex:8.1f} | {ex - dp:14.1f} {dp - en:11.1f}")
+print(f"{'kernel':8s} {'entry':>8s} {'dep-ok':>8s} {'exit':>8s} | {'run(dep->exit)':>14s} {'early-start':>11s} | "
+      f"{'1st data':>8s} {'last data':>9s} {'1st exit':>8s}  (GEMMs: operand bytes landed in smem)")
+f = lambda v: f"{v:8.1f}" if v is not None else "       -"
+for n, (en, dp, ex, fd, ld, fx) in zip(tl["names"], tl["last"]):
+    print(f"{n:8s} {en:8.1f} {dp:8.1f} {ex:8.1f} | {ex - dp:14.1f} {dp - en:11.1f} | {f(fd)} {f(ld)}  {f(fx)}")
 print(f"total {tl['last'][-1][2]:.1f} us")
