@@ -526,7 +526,7 @@ def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096
             e1.record()
             torch.cuda.synchronize(dev)
             ts.append(e0.elapsed_time(e1))
-        ms = statistics.median(ts[2:])
+        ms = statistics.median(ts[2:] or ts)
         out[name] = {"ms": ms, "gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak_gbs}
     return out
 
