@@ -350,7 +350,10 @@ gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restr
   const int64_t out_row = blockIdx.x;
   int64_t src_row = __ldg(indices + out_row);
   if (src_row < 0) src_row += num_src_rows;                       // torch index_select accepts negatives
-  if (src_row < 0 || src_row >= num_src_rows) return;             // (host validates; never read outside)
+  // An out-of-range index is never dereferenced (torch.index_select raises for it; detecting that here would
+  // need a device -> host round trip): the output row is ZERO-FILLED instead, so the result is deterministic.
+  const bool in_range = src_row >= 0 && src_row < num_src_rows;
+  if (!in_range) src_row = 0;
   const uint32_t total = t.chunk_begin[t.count];
   for (uint32_t base = blockIdx.y * (256u * kGatherUnroll) + threadIdx.x; base < total;
        base += gridDim.y * (256u * kGatherUnroll)) {
@@ -370,11 +373,11 @@ gather_rows_kernel(const __grid_constant__ GatherTable t, const int64_t* __restr
         char* d = t.dst[k] + out_row * t.dst_stride[k] + static_cast<int64_t>(c) * 16;
         const uint32_t left = t.row_bytes[k] - c * 16;
         if (t.vec16[k] && left >= 16) {
-          reg[j] = ld_stream_16(s);
+          reg[j] = in_range ? ld_stream_16(s) : make_uint4(0u, 0u, 0u, 0u);
           dptr[j] = d;
         } else {   // unaligned tensor or ragged row end: bytes
           const uint32_t nb = left < 16 ? left : 16;
-          for (uint32_t b = 0; b < nb; ++b) d[b] = s[b];
+          for (uint32_t b = 0; b < nb; ++b) d[b] = in_range ? s[b] : 0;
         }
       }
     }

@@ -141,7 +141,8 @@ AB200_API int32_t ab200_kv_rope_write_bulk(const void* const* kv_ptrs, int64_t k
  * (arctic_inference/vllm/swiftkv/llama_swiftkv.py:669-685) that compact hidden_states, residual,
  * positions, k_states and v_states to the surviving tokens.  Host arrays of num_tensors entries;
  * strides and row sizes in bytes; indices [num_indices] int64 on the device, each in
- * [-num_src_rows, num_src_rows) (out-of-range rows are skipped, never read). */
+ * [-num_src_rows, num_src_rows); an out-of-range index is never dereferenced and its output row is ZERO-FILLED
+ * (torch.index_select raises instead - detecting that would need a device -> host round trip). */
 AB200_API int32_t ab200_gather_rows(const void* const* src_ptrs, void* const* dst_ptrs,
                                     const int64_t* src_row_strides_bytes,
                                     const int64_t* dst_row_strides_bytes, const int64_t* row_bytes,

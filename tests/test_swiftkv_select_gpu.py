@@ -81,3 +81,21 @@ def test_swiftkv_select_step_matches_reference_sequence():
                           kv_cache_dtype="auto", k_scales=[], v_scales=[], num_kv_heads=Hkv, head_size=Dh,
                           logits_indices=logits_idx, graph_buffers=bufs, cuda_graph_max_batch_size=4)
     assert out2[0].shape[0] == B and torch.equal(out2[3], k.index_select(0, logits_idx))
+
+
+def test_gather_rows_out_of_range_index_is_zero_filled():
+    """an index outside [-rows, rows) is never dereferenced; its output row is zero-filled
+    (torch.index_select would raise - that check needs a device -> host sync this launch-only path avoids)."""
+    from arcticinference_b200 import swiftkv
+    DEVICE = torch.device("cuda:0")
+    a = torch.randn(10, 40, device=DEVICE).to(torch.bfloat16)          # 80-byte rows: vector + byte tails
+    b = torch.arange(10, device=DEVICE, dtype=torch.int64)
+    idx = torch.tensor([3, 10, -1, -11, 0, 99], device=DEVICE)
+    oa = torch.full((6, 40), 7.0, device=DEVICE, dtype=torch.bfloat16)
+    ob = torch.full((6,), 7, device=DEVICE, dtype=torch.int64)
+    ga, gb = swiftkv.gather_rows([a, b], idx, [oa, ob])
+    torch.cuda.synchronize()
+    assert torch.equal(ga[0], a[3]) and torch.equal(ga[2], a[9]) and torch.equal(ga[4], a[0])
+    for bad in (1, 3, 5):
+        assert not ga[bad].any() and gb[bad].item() == 0
+    assert gb.tolist() == [3, 0, 9, 0, 0, 0]
