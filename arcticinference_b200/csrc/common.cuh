@@ -58,7 +58,8 @@ struct Tune {
   int pdl = 1;             // programmatic dependent launch between the kernels of a draft step
   int umma_m64 = 1;        // <= 64 batch rows: UMMA M = 64 (8 KiB activation slot -> more stages)
   int gemm_2cta = 1;       // 129..256 rows: CTA-pair kernel (tcgen05 cta_group::2)
-  int rows_per_pass = 256; // batch rows that share one pass over the weights (128 / 256 / 512)
+  int rows_per_pass = 256; // batch rows per launch of the arg-max head / with fused token output (128 / 256)
+  int gate_mh2 = 1;        // store-epilogue GEMM: 257..512 rows in ONE CTA-pair launch (two m-blocks per tile)
   int late_trigger = 1;    // GEMMs signal their dependents only after their own dependency wait
   int pre_stages = -1;     // smem stages filled with W before the dependency wait (-1 = all)
   int l2_prefetch_kb = 0;  // extra W k-blocks prefetched into L2 before the dependency wait

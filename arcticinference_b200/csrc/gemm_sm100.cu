@@ -194,6 +194,7 @@ struct GemmParams {
   int32_t pre_stages;      // smem stages filled with W before the dependency wait
   int32_t late_trigger;    // 1: griddepcontrol.launch_dependents after the last TMA load
   int32_t m64;             // 1: UMMA M = 64 (MT == 1, <= 64 rows): row r lives in TMEM lane (r/16)*32 + r%16
+  int32_t mh;              // CTA-pair kernel: 256-row m-blocks that share one launch (1 or 2)
   int32_t kbs;             // k-blocks per pipeline stage = per TMA request (1: 2-D maps; 2: 3-D maps, MT == 1)
   uint32_t a_pitch;        // kbs == 2: bytes between the k-block slabs of the activation box (box rows * 128)
   uint32_t tx_bytes;    // bytes landing per stage
@@ -637,14 +638,20 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   const int num_kb = p.num_k_blocks;
   const int my_tiles = pair < p.num_n_tiles ? (p.num_n_tiles - 1 - pair) / npairs + 1 : 0;
+  // Batches of 257..512 rows: every weight tile is used for MH = 2 m-blocks of 256 rows back to back (work item =
+  // (tile, m-block), m-block fastest), each into its own TMEM accumulator buffer - ONE launch and one pass over
+  // the tile list instead of two launches that each stream all the weights (the second read of a tile comes from
+  // L2 where it still is; at these batches the kernel is tensor-bound either way).
+  const int MH = p.mh;
+  const int my_items = my_tiles * MH;
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      const int total = my_tiles * num_kb;
-      auto n0_of = [&](int g) { return (pair + (g / num_kb) * npairs) * p.block_n + static_cast<int>(rank) * half_n; };
+      const int total = my_items * num_kb;
+      auto n0_of = [&](int g) { return (pair + ((g / num_kb) / MH) * npairs) * p.block_n + static_cast<int>(rank) * half_n; };
       auto load_x = [&](int g, int stage) {
         tma_load_2d_2sm(smem_base + stage * stage_bytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK,
-                        static_cast<int>(rank) * kTileM, kEvictLast);
+                        ((g / num_kb) % MH) * 2 * kTileM + static_cast<int>(rank) * kTileM, kEvictLast);
       };
       auto load_w = [&](int g, int stage) {
         tma_load_2d_2sm(smem_base + stage * stage_bytes + kABytes, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK,
@@ -674,7 +681,7 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0; it < my_items; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // both CTAs' epilogues have drained this buffer
@@ -701,15 +708,19 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   } else {
     // ===================== epilogue (warps 2..5 of both CTAs) =====================
     const int quad = warp & 3;
-    const int row = static_cast<int>(rank) * kTileM + quad * 32 + lane;   // batch row of this thread
-    const bool row_ok = row < p.m_rows;
-    const bool warp_has_rows = static_cast<int>(rank) * kTileM + quad * 32 < p.m_rows;
-    float best = -INFINITY;
-    uint32_t best_idx = 0xFFFFFFFFu;
-    for (int it = 0; it < my_tiles; ++it) {
+    const int row_in_block = static_cast<int>(rank) * kTileM + quad * 32 + lane;   // row inside a 256-row m-block
+    float bests[2] = {-INFINITY, -INFINITY};
+    uint32_t best_idxs[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    for (int it = 0; it < my_items; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int n0 = (pair + it * npairs) * p.block_n;
+      const int mhi = it % MH;
+      const int n0 = (pair + (it / MH) * npairs) * p.block_n;
+      const int row = mhi * 2 * kTileM + row_in_block;                     // batch row of this thread
+      const bool row_ok = row < p.m_rows;
+      const bool warp_has_rows = mhi * 2 * kTileM + static_cast<int>(rank) * kTileM + quad * 32 < p.m_rows;
+      float best = mhi ? bests[1] : bests[0];
+      uint32_t best_idx = mhi ? best_idxs[1] : best_idxs[0];
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAcc;
@@ -750,12 +761,19 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           }
         }
       }
+      if (mhi) { bests[1] = best; best_idxs[1] = best_idx; }
+      else { bests[0] = best; best_idxs[0] = best_idx; }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
     }
     if constexpr (EPI == EPI_ARGMAX) {
-      if (row_ok && best_idx != 0xFFFFFFFFu) atomicMax(p.packed + row, pack_arg(best, best_idx));
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int row = m * 2 * kTileM + row_in_block;
+        if (m < MH && row < p.m_rows && best_idxs[m] != 0xFFFFFFFFu)
+          atomicMax(p.packed + row, pack_arg(bests[m], best_idxs[m]));
+      }
       if (p.tokens_out != nullptr) {
         const int et = threadIdx.x - 64;
         __threadfence();
@@ -982,6 +1000,7 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   const uint32_t fmt = KIND == KIND_BF16 ? 1u : 0u;
   // <= 64 rows: UMMA M = 64 halves the tensor-pipe work (and power) of this HBM-bound kernel
   p.m64 = m64 ? 1 : 0;
+  p.mh = 1;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
             (static_cast<uint32_t>((p.m64 ? 64 : kTileM) >> 4) << 24);
   p.x_scales = ax.x_scales;
@@ -1008,6 +1027,7 @@ template <int EPI>
 static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
                                  int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out, int64_t ldo,
                                  const ArgmaxExtra& ax, cudaStream_t s) {
+  const int mh = m_rows > 2 * kTileM ? 2 : 1;     // 257..512 rows: two 256-row m-blocks per weight tile
   static std::atomic<bool> attr_set[kMaxDevices];
   int rc = ensure_max_smem(gemm_tn_sm100_2cta<EPI>, attr_set, kSmemLimit);
   if (rc != AB200_OK) return rc;
@@ -1048,6 +1068,7 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.m64 = 0;
   p.kbs = 1;
   p.a_pitch = 0;
+  p.mh = mh;
   p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u);   // both CTAs
   // instruction descriptor: D = f32, A/B = bf16, K-major, N >> 3, M = 256 >> 4
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (16u << 24);
@@ -1068,6 +1089,16 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   return AB200_OK;
 }
 
+// Rows that share ONE launch.  Store-epilogue bf16 GEMM (gate / proj): 512 - the CTA-pair kernel runs two 256-row
+// m-blocks per weight tile (8B gate at B = 512: 82 -> 68 us).  Arg-max head: 256 per launch - it is tensor-bound
+// there (1.3 PFLOP/s = 0.92 of the sustained cuBLAS peak) and two launches were 2 % faster than the merged one.
+// fp8: 256 (the MT = 4 single-CTA shape is ingest-bound).
+static int rows_per_launch(int kind, int epi) {
+  const int r = gemm_rows_per_pass();
+  if (kind == KIND_BF16 && epi == EPI_STORE && r >= 256 && tune().gemm_2cta && tune().gate_mh2) return 512;
+  return r < 256 ? r : 256;
+}
+
 template <int EPI, int KIND = KIND_BF16>
 static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_rows, int64_t K,
                             int64_t ldx, int64_t ldw, int64_t n_valid, __nv_bfloat16* out,
@@ -1082,11 +1113,11 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
   AB200_REQUIRE(M > 0 && w_rows > 0 && K > 0 && n_valid > 0 && n_valid <= w_rows &&
                     w_rows < (1LL << 31) && K < (1LL << 31),
                 AB200_E_INVALID, "bf16 GEMM: bad sizes");
-  AB200_REQUIRE(ax.tokens_out == nullptr || (M <= gemm_rows_per_pass() && ax.done_counter != nullptr),
-                AB200_E_INVALID, "head_argmax: fused token output needs M <= %d and a done counter",
-                gemm_rows_per_pass());
-  for (int64_t m0 = 0; m0 < M; m0 += gemm_rows_per_pass()) {
-    const int64_t rows = M - m0 < gemm_rows_per_pass() ? M - m0 : gemm_rows_per_pass();
+  const int per_launch = rows_per_launch(KIND, EPI);
+  AB200_REQUIRE(ax.tokens_out == nullptr || (M <= per_launch && ax.done_counter != nullptr),
+                AB200_E_INVALID, "head_argmax: fused token output needs M <= %d and a done counter", per_launch);
+  for (int64_t m0 = 0; m0 < M; m0 += per_launch) {
+    const int64_t rows = M - m0 < per_launch ? M - m0 : per_launch;
     const char* xp = static_cast<const char*>(x) + m0 * ldx * esize;
     __nv_bfloat16* op = out ? out + m0 * ldo : nullptr;
     ArgmaxExtra a = ax;
@@ -1095,7 +1126,7 @@ static int launch_gemm_bf16(const void* x, const void* w, int64_t M, int64_t w_r
     int rc;
     if (rows <= kTileM)
       rc = launch_gemm_pass<EPI, 1, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
-    else if (rows <= 2 * kTileM && KIND == KIND_BF16 && tune().gemm_2cta)
+    else if (rows <= 4 * kTileM && KIND == KIND_BF16 && tune().gemm_2cta)
       rc = launch_gemm_pass_2cta<EPI>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
     else if (rows <= 2 * kTileM)
       rc = launch_gemm_pass<EPI, 2, KIND>(xp, w, rows, w_rows, K, ldx, ldw, n_valid, op, ldo, a, s);
@@ -1319,7 +1350,7 @@ extern "C" int32_t ab200_head_argmax_fp8(const void* xq, const float* x_scales, 
   ax.packed = reinterpret_cast<unsigned long long*>(packed_out);
   ax.x_scales = x_scales;
   ax.w_scale = w_scale;
-  if (tokens_out != nullptr && M <= gemm_rows_per_pass() && done_counter != nullptr) {
+  if (tokens_out != nullptr && M <= rows_per_launch(KIND_FP8, EPI_ARGMAX) && done_counter != nullptr) {
     ax.tokens_out = tokens_out;
     ax.tokens_stride = tokens_stride;
     ax.done_counter = done_counter;
