@@ -98,6 +98,12 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int32_t c0,
                "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* desc, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -295,8 +301,10 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       load_w(g, g);
     }
     const int l2_end = total < pre + p.l2_prefetch_kb ? total : pre + p.l2_prefetch_kb;
-    if (kbs == 1)
-      for (int g = pre; g < l2_end; ++g) tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
+    for (int g = pre; g < l2_end; ++g) {
+      if (kbs == 2) tma_prefetch_l2_3d(&tmap_w, 0, n0_of(g), 2 * (g % num_kb));
+      else tma_prefetch_l2_2d(&tmap_w, (g % num_kb) * kKElems, n0_of(g));
+    }
   }
   if (warp == 1) {
     if (lane == 0) {

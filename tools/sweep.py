@@ -224,7 +224,7 @@ def main():
     if not only or "gemm70" in only:
         sweep_gemm(rows, 128256, 8192, 8192, [64, 128, 256], [32])
     if not only or "gemmoss" in only:
-        sweep_gemm(rows, 201088, 2880, 2880, [64, 512], [32])
+        sweep_gemm(rows, 201088, 2880, 2880, [64, 128, 256, 512], [32])
     if not only or "cell" in only:
         sweep_cell(rows, 4096, 128256, [1, 64, 256, 1024, 4096, 16384])
     if not only or "kv" in only:
