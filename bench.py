@@ -540,9 +540,12 @@ def make_speculator(V, H, D, S, max_bs, dev, seed=0, **kw):
     return model
 
 
-def spec_bytes(V_rows, H, D, S, B):
-    """Algorithmic bytes of one S-step proposal: weights streamed once per step + activations."""
+def spec_bytes(V_rows, H, D, S, B, fp8_head=False):
+    """Algorithmic bytes of one S-step proposal: weights streamed once per step + activations.
+    fp8_head: the e4m3 qhead streams one byte per weight (and reads the e4m3 copy of the state + its scales)."""
     head = V_rows * D * 2 + B * D * 2 + 8 * B
+    if fp8_head:
+        head = V_rows * D + B * D + 12 * B
     gate0 = 4 * D * H * 2 + B * H * 2 + B * 4 * D * 2
     gate = 4 * D * D * 2 + B * D * 2 + B * 4 * D * 2
     cell = B * D * 2 * 8 + 4 * D * 2 + 8 * B
@@ -594,9 +597,10 @@ def bench_cfg3_70b(dev, world, rank, steps, warmup, peak):
         ms = time_resident_proposals(model, B, S, steps, warmup, 3000 + rank, dev)
         max_ms, units = replicas.aggregate(ms, B * S * steps, dev)
         per = max_ms / steps
-        nbytes = spec_bytes(dict(model.named_parameters())["head.0.weight"].shape[0], H, D, S, B)
+        nbytes = spec_bytes(dict(model.named_parameters())["head.0.weight"].shape[0], H, D, S, B, model.uses_fp8_head(B))
         flops = 2 * B * (4 * D * H + (S - 1) * 4 * D * D + S * D * V)
         out[f"D{D}"] = {"ms_per_proposal": per, "value": units / max_ms * 1e3, "unit": UNIT,
+                        "head": "FP8 qhead (padded batch <= 32: the reference's rule)" if model.uses_fp8_head(B) else "bf16",
                         "algorithmic_bytes_per_gpu": nbytes, **roofline_of(B, nbytes, flops, per, peak)}
         del model
         torch.cuda.empty_cache()
@@ -617,15 +621,17 @@ def bench_cfg4_gptoss(dev, world, rank, steps, warmup, peak):
     V, H, D, S, Bg = (CFG4[k] for k in ("V", "H", "D", "S", "B_global"))
     B = (Bg + world - 1) // world
     model = make_speculator(V, H, D, S, B, dev)
+    fp8_rule = model.uses_fp8_head(B)
     ms = time_resident_proposals(model, B, S, steps, warmup, 4000 + rank, dev)
     max_ms, units = replicas.aggregate(ms, B * S * steps, dev)
     per = max_ms / steps
-    nbytes = spec_bytes(dict(model.named_parameters())["head.0.weight"].shape[0], H, D, S, B)
+    nbytes = spec_bytes(dict(model.named_parameters())["head.0.weight"].shape[0], H, D, S, B, fp8_rule)
     out = {"workload": f"GPT-OSS-120B-shaped speculator (H=D={H}, V={V}), bf16, GLOBAL batch {Bg} split over "
                        f"{world} GPU(s), {S} spec tokens + SwiftKV bulk KV write 18 layers x 32768 tokens per GPU",
            "scaling": "strong (speculator batch) / weak (KV write: every GPU writes its own 32K-token cache)",
            "per_gpu_batch": B, "padded_graph_batch": padding_size(B), "steps": steps,
            "speculator": {"ms_per_proposal": per, "value": units / max_ms * 1e3, "unit": UNIT,
+                          "head": "FP8 qhead (padded batch <= 32: the reference's rule)" if fp8_rule else "bf16",
                           "algorithmic_bytes_per_gpu": nbytes,
                           **roofline_of(B, nbytes, 2 * B * (4 * D * H + (S - 1) * 4 * D * D + S * D * V), per, peak)}}
     del model
