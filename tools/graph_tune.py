@@ -46,13 +46,22 @@ def replay_us():
     return statistics.median(ts), min(ts)
 
 
+def per_kernel():
+    """median dep->exit per kernel kind from the device-side trace (resolution ~0.1 us, unlike the replay time)"""
+    tl = bench.device_timeline(model, ids, hid, B, S, replays=9)
+    out = {}
+    for n, v in zip(tl["names"], tl["run_us"]):
+        out.setdefault(n.rstrip("0123456789"), []).append(v)
+    return " ".join(f"{k}={statistics.median(v):.2f}" for k, v in out.items()) + f" | traced replay {tl['replay_us']:.1f}"
+
+
 base = replay_us()
-print(f"B={B} defaults: {base[0]:.1f} us (min {base[1]:.1f})", flush=True)
+print(f"B={B} defaults: {base[0]:.1f} us (min {base[1]:.1f}) | {per_kernel()}", flush=True)
 for name, values in sweeps:
     for v in values:
         assert lib.ab200_debug_set_tunable(name.encode(), v) == 0, name
         med, mn = replay_us()
-        print(f"  {name}={v}: {med:.1f} us (min {mn:.1f})", flush=True)
+        print(f"  {name}={v}: {med:.1f} us (min {mn:.1f}) | {per_kernel()}", flush=True)
     # back to the compiled-in default of this tunable (first value listed is expected to be the default)
     lib.ab200_debug_set_tunable(name.encode(), values[0])
 again = replay_us()
