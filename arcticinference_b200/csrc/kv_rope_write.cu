@@ -27,8 +27,9 @@
 //   (i, i + rot/2) inside a head - the partner 16-byte unit lives in lane ^ (rot/16) of the same warp and is
 //   fetched by shuffle; GPT-J style pairs (2i, 2i+1) are in-lane.
 //
-// Work split like kv_write.cu: tokens on grid.x, a token's (layer, 16-byte unit) space split evenly over
-// grid.y, every thread keeps kRopeUnroll independent 16-byte loads in flight before its first store;
+// Work split like kv_write.cu: tokens on grid.x, a token's (layer, 16-byte K unit) space split evenly over
+// grid.y; a thread moves kRopeUnroll K units and the matching V units, all 2 x kRopeUnroll 16-byte loads in flight
+// before its first store;
 // per-layer pointers travel by value.  HBM-bound: algorithmic bytes = T * L * 2n * (e + e_cache) + 16 T.
 #include "common.cuh"
 #include "kv_common.cuh"
@@ -37,7 +38,7 @@ namespace ab200 {
 
 constexpr int kRopeMaxLayers = 64;     // 5 pointers per layer = 2.5 KiB of kernel-parameter space
 constexpr int kRopeThreads = 256;
-constexpr int kRopeUnroll = 8;
+constexpr int kRopeUnroll = 4;          // K units per thread; the same thread moves the matching V units
 
 struct RopeTable {
   const char* kv[kRopeMaxLayers];   // kv_proj output of the layer: rows [k (n) | ... | v (n)]
@@ -57,13 +58,13 @@ struct RopeParams {
   uint32_t rot_dim;            // elements rotated per head
   uint32_t head_units;         // head_size / 8
   uint32_t n_units;            // n / 8: 16-byte units of K (and of V) per layer
-  int32_t u_shift;             // log2(2 * n_units) when that is a power of two, else -1
+  int32_t u_shift;             // log2(n_units) when that is a power of two, else -1
   const int64_t* slot_mapping; // [T]
   int64_t num_tokens;
   int64_t block_stride_bytes;  // cache bytes between blocks
   int32_t block_size;          // encoded (kv_common.cuh)
   uint32_t cache_row_bytes;    // n * cache element size
-  uint32_t total_units;        // layers * 2 * n_units
+  uint32_t total_units;        // layers * n_units: (layer, K unit) work items (each also moves its V unit)
   uint32_t per_cta;            // units per CTA of grid.y (multiple of kRopeThreads)
   // compact rows of the surviving tokens (optional)
   const int64_t* sel_indices;  // [num_sel] token indices (negative wraps like torch.index_select)
@@ -147,9 +148,11 @@ kv_rope_write_kernel(const __grid_constant__ RopeTable tbl, const __grid_constan
   const uint32_t half_units = p.rot_dim >> 4;           // 16-byte units in one half of the rotated span
   const uint32_t rot_units = p.rot_dim >> 3;
 
+  // Work item q = (layer, 16-byte unit u of the layer's K row); the SAME thread also moves unit u of the V row,
+  // so K work (exchange + rotation) and V work (copy) never share a branch and no lane shuffles for V.
   const uint32_t q0 = blockIdx.y * p.per_cta + threadIdx.x;
   const uint32_t q_end = min(p.total_units, (blockIdx.y + 1) * p.per_cta);
-  const uint32_t U = 2 * p.n_units;
+  const uint32_t U = p.n_units;
 
   // The thread's unit position inside a head is the same in every iteration (per_cta, kRopeThreads and U are
   // multiples of head_units, a power of two <= 32): its cos / sin vectors are loaded once.
@@ -177,42 +180,41 @@ kv_rope_write_kernel(const __grid_constant__ RopeTable tbl, const __grid_constan
     }
   }
 
-  uint4 reg[kRopeUnroll];
+  uint4 kreg[kRopeUnroll], vreg[kRopeUnroll];
   const int64_t tok_off = token * p.kv_row_bytes;
 #pragma unroll
   for (int j = 0; j < kRopeUnroll; ++j) {
     const uint32_t q = q0 + j * kRopeThreads;
     if (q < q_end) {
       const uint32_t layer = p.u_shift >= 0 ? q >> p.u_shift : q / U, u = q - layer * U;
-      const bool is_k = u < p.n_units;
-      const uint32_t byte_in_row = is_k ? u * 16u : p.v_off_bytes + (u - p.n_units) * 16u;
-      reg[j] = ld_stream_16(tbl.kv[layer] + tok_off + byte_in_row);
+      const char* row = tbl.kv[layer] + tok_off + u * 16u;
+      kreg[j] = ld_stream_16(row);
+      vreg[j] = ld_stream_16(row + p.v_off_bytes);
     } else {
-      reg[j] = make_uint4(0, 0, 0, 0);
+      kreg[j] = make_uint4(0, 0, 0, 0);
+      vreg[j] = make_uint4(0, 0, 0, 0);
     }
   }
 #pragma unroll
   for (int j = 0; j < kRopeUnroll; ++j) {
     const uint32_t q = q0 + j * kRopeThreads;
     const bool live = q < q_end;
-    const uint32_t layer = live ? (p.u_shift >= 0 ? q >> p.u_shift : q / U) : 0, u = live ? q - layer * U : 0;
-    const bool is_k = live && u < p.n_units;
-    uint4 val = reg[j];
+    uint4 val = kreg[j];
     if constexpr (NEOX) {
-      // every lane takes part in the exchange (warp-uniform trip count); only rotating K units use it
+      // every lane takes part in the exchange (warp-uniform trip count)
       uint4 other;
       other.x = __shfl_xor_sync(0xffffffffu, val.x, half_units);
       other.y = __shfl_xor_sync(0xffffffffu, val.y, half_units);
       other.z = __shfl_xor_sync(0xffffffffu, val.z, half_units);
       other.w = __shfl_xor_sync(0xffffffffu, val.w, half_units);
-      if (is_k && rotates) {
+      if (rotates) {
         val.x = rot_word<T, STORAGE>(val.x, other.x, cosv.x, sinv.x, sign);
         val.y = rot_word<T, STORAGE>(val.y, other.y, cosv.y, sinv.y, sign);
         val.z = rot_word<T, STORAGE>(val.z, other.z, cosv.z, sinv.z, sign);
         val.w = rot_word<T, STORAGE>(val.w, other.w, cosv.w, sinv.w, sign);
       }
     } else {
-      if (is_k && rotates) {
+      if (rotates) {
         val.x = rot_word<T, STORAGE>(val.x, __byte_perm(val.x, 0, 0x1032), cosv.x, sinv.x, sign);
         val.y = rot_word<T, STORAGE>(val.y, __byte_perm(val.y, 0, 0x1032), cosv.y, sinv.y, sign);
         val.z = rot_word<T, STORAGE>(val.z, __byte_perm(val.z, 0, 0x1032), cosv.z, sinv.z, sign);
@@ -220,20 +222,24 @@ kv_rope_write_kernel(const __grid_constant__ RopeTable tbl, const __grid_constan
       }
     }
     if (!live) continue;
-    const uint32_t c = is_k ? u : u - p.n_units;        // 16-byte unit inside the (token, layer) row
+    const uint32_t layer = p.u_shift >= 0 ? q >> p.u_shift : q / U, u = q - layer * U;
     if (to_cache) {
       if constexpr (KVD == 0) {
-        char* base = is_k ? tbl.k[layer] : tbl.v[layer];
-        st_stream_16(base + dst_row + static_cast<int64_t>(c) * 16, val);
+        const int64_t d = dst_row + static_cast<int64_t>(u) * 16;
+        st_stream_16(tbl.k[layer] + d, val);
+        st_stream_16(tbl.v[layer] + d, vreg[j]);
       } else {
-        const float s = __ldg(is_k ? tbl.ks[layer] : tbl.vs[layer]);
-        const uint2 qv = quant_chunk<Pk<T>::kSrc, KVD == 2>(val, s, __frcp_rn(s));
-        char* base = is_k ? tbl.k[layer] : tbl.v[layer];
-        *reinterpret_cast<uint2*>(base + dst_row + static_cast<int64_t>(c) * 8) = qv;
+        const float sk = __ldg(tbl.ks[layer]), sv = __ldg(tbl.vs[layer]);
+        const uint2 qk = quant_chunk<Pk<T>::kSrc, KVD == 2>(val, sk, __frcp_rn(sk));
+        const uint2 qv = quant_chunk<Pk<T>::kSrc, KVD == 2>(vreg[j], sv, __frcp_rn(sv));
+        const int64_t d = dst_row + static_cast<int64_t>(u) * 8;
+        *reinterpret_cast<uint2*>(tbl.k[layer] + d) = qk;
+        *reinterpret_cast<uint2*>(tbl.v[layer] + d) = qv;
       }
     } else {
-      char* base = is_k ? p.k_states_out : p.v_states_out;
-      st_stream_16(base + out_row * p.states_row_bytes + (static_cast<int64_t>(layer) * p.n_units + c) * 16, val);
+      const int64_t d = out_row * p.states_row_bytes + (static_cast<int64_t>(layer) * p.n_units + u) * 16;
+      st_stream_16(p.k_states_out + d, val);
+      st_stream_16(p.v_states_out + d, vreg[j]);
     }
   }
 }
@@ -326,13 +332,13 @@ extern "C" int32_t ab200_kv_rope_write_bulk(const void* const* kv_ptrs, int64_t 
     p.n_units = static_cast<uint32_t>(n / 8);
     p.u_shift = -1;
     for (int sh = 0; sh < 31; ++sh)
-      if ((1u << sh) == 2u * p.n_units) p.u_shift = sh;
+      if ((1u << sh) == p.n_units) p.u_shift = sh;
     p.slot_mapping = slot_mapping;
     p.num_tokens = num_tokens;
     p.block_stride_bytes = block_stride * ce;
     p.block_size = encode_block_size(block_size);
     p.cache_row_bytes = static_cast<uint32_t>(n * ce);
-    p.total_units = static_cast<uint32_t>(layers) * 2u * p.n_units;
+    p.total_units = static_cast<uint32_t>(layers) * p.n_units;
     const uint32_t cap = kRopeThreads * kRopeUnroll;
     const uint32_t gy = (p.total_units + cap - 1) / cap;
     // even split over grid.y, rounded up to whole CTAs-worth of threads so that a thread's unit position
