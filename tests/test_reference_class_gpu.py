@@ -83,3 +83,52 @@ def test_reference_class_fp32_exact_tokens(spec):
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old
         assert torch.equal(m.generate_proposals(ids, hid, S), exp)
+
+
+def test_one_call_drop_in_patches_the_reference_class(spec):
+    """arcticinference_b200.integration.patch_lstm_speculator(): the UNMODIFIED reference module, patched at run time
+    (INTEGRATION.md 2a), returns the native loop's tokens through its own generate_proposals; other configurations
+    (here: a CPU call) keep running the reference's code."""
+    from arcticinference_b200 import integration
+    V, H, D, S, B = 32000, 1024, 512, 3, 24
+    w = O.make_weights(V, H, D, torch.bfloat16, seed=0, device=DEV)
+    cls = spec.ArcticLSTMSpeculator
+    with torch.inference_mode():
+        ref = ref_class.build_reference(spec, V, H, D, S, B, torch.bfloat16, w, device=DEV)
+        ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=11, device=DEV)
+        before = ref.generate_proposals(ids, hid, S).clone()
+        try:
+            assert integration.patch_lstm_speculator(cls) is cls
+            assert integration.patch_lstm_speculator(cls) is cls                      # idempotent
+            after = ref.generate_proposals(ids, hid, S)
+            twin = ref._b200_impl
+            assert twin.qhead is None                                                 # ref.qhead is None -> bf16 head
+            assert torch.equal(after, twin.generate_proposals(ids, hid, S))
+            assert (after == before).float().mean().item() >= 0.999
+            with pytest.raises(ValueError, match="Max speculative tokens"):           # same error contract
+                ref.generate_proposals(ids, hid, S + 1)
+            # new weights in the same storage (what load_weights does): the twin must not serve stale values
+            w2 = O.make_weights(V, H, D, torch.bfloat16, seed=5, device=DEV)
+            for k, p in ref.named_parameters():
+                p.data.copy_(w2[k])
+            ref._b200_impl = None
+            fresh = ref.generate_proposals(ids, hid, S)
+            assert not torch.equal(fresh, after)
+            port = O.RefLSTMSpeculator(w2, V, S).generate_proposals(ids, hid, S)
+            assert (fresh == port).float().mean().item() >= 0.999
+        finally:
+            integration.unpatch_lstm_speculator(cls)
+        assert not getattr(cls.generate_proposals, "_b200_patched", False)
+        assert torch.equal(ref.generate_proposals(ids, hid, S), port)                 # the reference's own code again
+
+
+def test_one_call_drop_in_patches_py_custom_ops():
+    import types
+    from arcticinference_b200 import integration, py_custom_ops
+    fake = types.ModuleType("arctic_inference.py_custom_ops")
+    fake.try_load_torch_library = lambda: False
+    fake.reshape_and_cache_flash_bulk = None
+    assert integration.patch_py_custom_ops(fake) is True
+    assert fake.try_load_torch_library is py_custom_ops.try_load_torch_library
+    assert fake.reshape_and_cache_flash_bulk is py_custom_ops.reshape_and_cache_flash_bulk
+    assert fake.try_load_torch_library() is True
