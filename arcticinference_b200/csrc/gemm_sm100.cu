@@ -437,10 +437,9 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
         const bool row_ok = lane_used && row < p.m_rows;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * MT + t) * kAccSlot;
         if (t * kTileM + warp_row0 >= p.m_rows) continue;  // whole warp out of range (warp-uniform)
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
+        // One 16-column chunk; the TMEM load of the NEXT chunk is already in flight while this runs
+        // (double-buffered registers: the epilogue was a serial ld -> wait -> convert -> store chain).
+        auto process = [&](uint32_t (&r)[16], int c0) {
           if constexpr (KIND == KIND_FP8) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(sa[t] * (sb * __uint_as_float(r[j])));
@@ -477,6 +476,19 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
                 }
               }
             }
+          }
+        };
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 16 < p.block_n;          // warp-uniform
+          if (has_b) tmem_ld16(taddr + c0 + 16, rb);
+          process(ra, c0);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < p.block_n) tmem_ld16(taddr + c0 + 32, ra);
+            process(rb, c0 + 16);
           }
         }
       }
@@ -697,6 +709,10 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);          // the bytes of both CTAs have landed
           tc_fence_after();
+          if (p.trace != nullptr && lane == 0) {
+            if (it == 0 && kb == 0) trace_stamp(p.trace, 3);
+            if (it == my_items - 1 && kb == num_kb - 1) trace_stamp(p.trace, 4);
+          }
           if (elect_one()) {
             const uint32_t sa = smem_base + stage * stage_bytes;
             const uint64_t da = smem_desc_sw128(sa);
@@ -733,10 +749,7 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAcc;
       if (warp_has_rows) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
+        auto process = [&](uint32_t (&r)[16], int c0) {
           const int col0 = n0 + c0;
           if constexpr (EPI == EPI_STORE) {
             if (row_ok && col0 < p.n_valid) {
@@ -766,6 +779,19 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 }
               }
             }
+          }
+        };
+        uint32_t ra[16], rb[16];
+        tmem_ld16(taddr, ra);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 16 < p.block_n;          // warp-uniform
+          if (has_b) tmem_ld16(taddr + c0 + 16, rb);
+          process(ra, c0);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < p.block_n) tmem_ld16(taddr + c0 + 32, ra);
+            process(rb, c0 + 16);
           }
         }
       }
@@ -812,7 +838,10 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
-  if (threadIdx.x == 0) trace_stamp(p.trace, 2);
+  if (threadIdx.x == 0) {
+    trace_stamp(p.trace, 2);
+    trace_stamp(p.trace, 5);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -1052,6 +1081,8 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
       bn = c;
     }
   }
+  const int forced_bn = EPI == EPI_STORE ? tune().gate_block_n : tune().head_block_n;   // debug sweeps only
+  if (forced_bn >= 32 && forced_bn <= 256 && forced_bn % 32 == 0) bn = forced_bn;
   const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
   const uint32_t stage_bytes = kABytes + (bn / 2) * 128;
   int stages = (kSmemLimit - 1024 - 256) / stage_bytes;

@@ -94,6 +94,12 @@ if what in ("gate", "all"):
         rows.append(run_case(64, 16384, 4096, False, warm_x=True, **{**DEFAULTS, "max_stages": stg}))
     for bn in (40, 48, 64, 80, 96):
         rows.append(run_case(64, 11520, 2880, False, warm_x=True, **{**DEFAULTS, "gate_block_n": bn}))
+if what in ("pair",):
+    # CTA-pair kernel (129..512 rows): where the cases that lose to cuBLAS spend their time
+    for (M, N, K) in ((256, 16384, 4096), (512, 16384, 4096), (256, 11520, 2880), (512, 11520, 2880), (256, 32768, 8192)):
+        rows.append(run_case(M, N, K, False, warm_x=True, **DEFAULTS))
+        for bn in (96, 128, 192, 256):
+            rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "gate_block_n": bn}))
 if what in ("head", "all"):
     for kbs in (1, 2):
         rows.append(run_case(64, 128256, 4096, True, warm_x=True, **{**DEFAULTS, "head_kbs": kbs}))
@@ -102,7 +108,8 @@ if what in ("head", "all"):
         rows.append(run_case(64, 128256, 4096, True, warm_x=True, **{**DEFAULTS, "head_kbs": 2, "head_block_n": bn}))
 tune(**DEFAULTS)
 # cuBLAS reference for the gate shapes, same timing method
-for (M, N, K) in ((64, 16384, 4096), (128, 16384, 4096), (64, 11520, 2880)):
+for (M, N, K) in ((64, 16384, 4096), (128, 16384, 4096), (64, 11520, 2880), (256, 16384, 4096), (512, 16384, 4096),
+                  (256, 11520, 2880), (512, 11520, 2880)):
     x = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
     for _ in range(3):
