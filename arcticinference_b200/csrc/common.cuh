@@ -66,7 +66,6 @@ struct Tune {
   int gate_block_n = 0;    // debug: force the tile width of the store-epilogue GEMM (0 = heuristic)
   int head_block_n = 0;    // debug: force the tile width of the arg-max GEMM
   int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)
-  int early_producer = 1;  // TMA producer starts streaming W before TMEM allocation completes
   int gate_kbs = 2;        // k-blocks per TMA request / pipeline stage of the store-epilogue GEMM (1 or 2)
   int head_kbs = 2;        // ... of the arg-max (vocab head) GEMM (applies to <= 64 rows only)
 };
