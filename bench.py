@@ -74,8 +74,9 @@ def shared_config(world: int) -> dict:
             "global_batch": B * world, "n_gpus": world, "scaling": "weak",
             "parallelism": f"{world} independent replica(s), no data-path collective",
             "l2": "inputs larger than L2: 3.57 GB of weights streamed per step vs 126 MB L2",
-            "reference_arm": "the reference's CPU PyTorch path (oracle port), ONE process on rank 0 with all "
-                             "host threads at every N; a bounded sample of the same workload"}
+            "reference_arm": "the reference's CPU PyTorch path (the unmodified class when its sources travelled, else "
+                             "its op-for-op port), ONE process on rank 0 with all host threads at every N; a bounded "
+                             "sample of the same workload"}
 
 
 def measured_tflops_sustained():
@@ -178,9 +179,14 @@ def synthetic_weights(model, seed: int):
     model.load_weights(ws.items())
 
 
+_CPU_REF_KIND = {"kind": "port"}
+
+
 def cpu_reference_run(steps: int, warmup: int, weights=None, budget_s: float = 150.0, batch: int = None):
-    """The reference's CPU PyTorch path (oracle port, all host threads) on the bench config.
-    Returns (tokens_per_s, ms_per_step, sample description, threads)."""
+    """The reference's CPU PyTorch path on the bench config, all host threads: the UNMODIFIED reference class
+    (arctic_speculator.py::ArcticLSTMSpeculator, eager, qhead = None) when its sources travelled with the repo
+    (baseline/_ref, oracle/ref_class.py) - kind "reference" - else the op-for-op port (bit-exact to it on the CPU,
+    tests/test_oracle_speculator.py) - kind "port".  Returns (tokens_per_s, ms_per_step, sample description, threads)."""
     import torch
     from oracle import speculator_ref as O
     V, H, D, S, B = (CFG[k] for k in "VHDSB")
@@ -188,7 +194,18 @@ def cpu_reference_run(steps: int, warmup: int, weights=None, budget_s: float = 1
     torch.set_num_threads(os.cpu_count() or 1)
     if weights is None:
         weights = O.make_weights(V, H, D, torch.bfloat16, seed=0)
-    ref = O.RefLSTMSpeculator(weights, V, S)
+    ref = None
+    try:
+        from oracle import ref_class
+        if ref_class.reference_root() is not None:
+            ref = ref_class.build_reference(ref_class.load_reference_module(), V, H, D, S, CFG["B"], torch.bfloat16,
+                                            {k: v for k, v in weights.items()}, device="cpu")
+            _CPU_REF_KIND["kind"] = "reference"
+    except Exception:  # noqa: BLE001 - vLLM import trouble on this box: the port is the same arithmetic
+        ref = None
+    if ref is None:
+        ref = O.RefLSTMSpeculator(weights, V, S)
+        _CPU_REF_KIND["kind"] = "port"
     ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=1)
     with torch.inference_mode():
         t0 = time.perf_counter()
@@ -208,7 +225,8 @@ def cpu_reference_run(steps: int, warmup: int, weights=None, budget_s: float = 1
         for _ in range(steps):
             ref.generate_proposals(ids[:b], hid[:b], S)
         dt = time.perf_counter() - t0
-    sample = (f"{steps} proposals of batch {b} x {S} draft tokens, bf16, 8B shape, torch CPU "
+    what = "unmodified reference class" if _CPU_REF_KIND["kind"] == "reference" else "oracle port of the reference class"
+    sample = (f"{steps} proposals of batch {b} x {S} draft tokens, bf16, 8B shape, {what}, torch CPU "
               f"({torch.get_num_threads()} threads)")
     return b * S * steps / dt, dt / steps * 1e3, sample, torch.get_num_threads()
 
@@ -223,8 +241,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": shared_config(args.gpus),
-        "arm": {"where": "host CPU cores (reference PyTorch path, oracle port)", "ranks_working": 1},
-        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "arm": {"where": "host CPU cores (the reference's PyTorch path: " + _CPU_REF_KIND["kind"] + ")", "ranks_working": 1},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": _CPU_REF_KIND["kind"], "sample": sample},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -1073,7 +1091,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu_w = {k: v.cpu() for k, v in model.named_parameters()}
         tps, ms, sample, threads = cpu_reference_run(steps=40, warmup=2, weights=cpu_w, budget_s=25.0)
-        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": threads, "kind": _CPU_REF_KIND["kind"],
                                 "sample": sample, "ms_per_step": ms}
         # BASELINE configs[0]: the reference's CPU path at batch 1
         t1, ms1, sample1, _ = cpu_reference_run(steps=8, warmup=2, weights=cpu_w, budget_s=1e9, batch=1)

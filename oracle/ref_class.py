@@ -17,6 +17,7 @@ tracked tree.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import shutil
 import sys
@@ -94,9 +95,10 @@ def load_reference_module(root: str | None = None):
     f8.Fp8ConfigWithEmbedding = Fp8ConfigWithEmbedding
     f8.OriginalFp8LinearMethod = OriginalFp8LinearMethod
     sys.modules[f8.__name__] = f8
-    import vllm.envs as envs                                             # stub 3
+    with contextlib.redirect_stdout(sys.stderr):                        # importing vLLM may print; stdout is the caller's
+        import vllm.envs as envs                                         # stub 3
+        import vllm.distributed.parallel_state as ps                     # stub 4
     envs.VLLM_USE_V1 = True
-    import vllm.distributed.parallel_state as ps                         # stub 4
 
     class G:
         world_size = 1
@@ -111,7 +113,8 @@ def load_reference_module(root: str | None = None):
 
     ps._TP = G()
     ps._SP = G()
-    import arctic_inference.vllm.spec_dec.arctic_speculator as spec
+    with contextlib.redirect_stdout(sys.stderr):
+        import arctic_inference.vllm.spec_dec.arctic_speculator as spec
     _SPEC = spec
     return spec
 
@@ -141,7 +144,8 @@ def build_reference(spec, V, H, D, n_predict, max_bs, dtype, weights, device="cp
     old_dtype = torch.get_default_dtype()
     torch.set_default_dtype(dtype)                   # the class allocates with the default dtype / device (:592-605)
     try:
-        with torch.device(device):
+        # the class prints while constructing ("CREATED NEXT PREVIOUS HIDDEN STATES", :607): keep the caller's stdout clean
+        with torch.device(device), contextlib.redirect_stdout(sys.stderr):
             model = spec.ArcticLSTMSpeculator(vllm_config=vc)
     finally:
         torch.set_default_dtype(old_dtype)
