@@ -76,15 +76,17 @@ select_hidden_rows_kernel(const char* __restrict__ hidden, int64_t row_stride_by
   int64_t src = (gen - 1) + __ldg(row_offsets + r);
   // gen == 0 indexes row offset-1 in the reference (negative wraps in torch); clamp into the tensor
   if (src < 0) src += num_rows;
-  if (src < 0 || src >= num_rows) return;
-  const char* s = hidden + src * row_stride_bytes;
+  // an index outside the tensor (the reference's fancy indexing would raise) is never dereferenced: the output
+  // row is zero-filled, so the result is deterministic
+  const bool ok = src >= 0 && src < num_rows;
+  const char* s = hidden + (ok ? src : 0) * row_stride_bytes;
   char* d = out + r * out_stride_bytes;
   if (vec16) {
     for (uint32_t q = threadIdx.x; q < row_bytes / 16; q += blockDim.x)
-      st_stream_16(d + q * 16ull, ld_stream_16(s + q * 16ull));
-    for (uint32_t b = (row_bytes / 16) * 16 + threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = s[b];
+      st_stream_16(d + q * 16ull, ok ? ld_stream_16(s + q * 16ull) : make_uint4(0u, 0u, 0u, 0u));
+    for (uint32_t b = (row_bytes / 16) * 16 + threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = ok ? s[b] : 0;
   } else {
-    for (uint32_t b = threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = s[b];
+    for (uint32_t b = threadIdx.x; b < row_bytes; b += blockDim.x) d[b] = ok ? s[b] : 0;
   }
 }
 
