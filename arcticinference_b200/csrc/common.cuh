@@ -62,7 +62,8 @@ struct Tune {
   int gate_mh2 = 1;        // store-epilogue GEMM: 257..512 rows in ONE CTA-pair launch (two m-blocks per tile)
   int late_trigger = 1;    // GEMMs signal their dependents only after their own dependency wait
   int pre_stages = -1;     // smem stages filled with W before the dependency wait (-1 = all)
-  int l2_prefetch_kb = 0;  // extra W k-blocks prefetched into L2 before the dependency wait
+  int l2_prefetch_kb = 0;  // arg-max GEMM: extra W pipeline steps prefetched into L2 before the dependency wait
+  int gate_l2_prefetch = 0; // store-epilogue GEMM: the same
   int gate_block_n = 0;    // debug: force the tile width of the store-epilogue GEMM (0 = heuristic)
   int head_block_n = 0;    // debug: force the tile width of the arg-max GEMM
   int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)

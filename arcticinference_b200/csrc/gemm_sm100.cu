@@ -1026,7 +1026,7 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
   p.kbs = kbs;
   p.a_pitch = static_cast<uint32_t>(box_m) * 128u;
   p.stages = stages;
-  p.l2_prefetch_kb = pdl_enabled() ? tune().l2_prefetch_kb : 0;
+  p.l2_prefetch_kb = pdl_enabled() ? (EPI == EPI_STORE ? tune().gate_l2_prefetch : tune().l2_prefetch_kb) : 0;
   p.late_trigger = gemm_late_trigger();
   p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
