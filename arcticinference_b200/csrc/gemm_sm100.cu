@@ -4,17 +4,21 @@
 //   argmax_n ( x[M, K] . w[N, K]^T )       vocab head + greedy pick, logits never materialised
 //                                          (logits_processor_opt.py:83-107, arctic_speculator.py:726-732)
 //
-// Regime: M = draft batch (<= 128 per pass), N = 4D or the padded vocab, K = H or D.  The weight
-// matrix is streamed from HBM exactly once per call and dominates traffic (bytes = N*K*2), so the
-// kernel is a weight-streaming pipeline whose job is to keep HBM saturated:
-//   * warp 0  : TMA producer - cp.async.bulk.tensor 2D boxes (SWIZZLE_128B) of x [box_m x 64] and
-//               w [block_n x 64] into a multi-stage smem ring, mbarrier complete_tx signalling;
+// Regime: M = draft batch (<= 128 per single-CTA launch, <= 512 per CTA-pair launch), N = 4D or the padded vocab,
+// K = H or D.  The weight matrix is streamed from HBM exactly once per call and dominates traffic (bytes = N*K*2), so
+// the kernel is a weight-streaming pipeline whose job is to keep HBM saturated:
+//   * warp 0  : TMA producer - cp.async.bulk.tensor boxes (SWIZZLE_128B) of x [box_m x 64] and w [block_n x 64] into a
+//               multi-stage smem ring, mbarrier complete_tx signalling.  It owns the stage barriers and starts
+//               streaming W before TMEM is allocated and long before the dependency wait (the weights never depend
+//               on the previous kernel).  Where it pays, ONE 3-D request brings TWO k-blocks per operand (kbs = 2):
+//               the per-SM rate of TMA requests, not HBM, bounded the narrow-tile GEMMs (profiles/r2_gemm_tune.md);
 //   * warp 1  : MMA issuer   - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//               (M=128, N=block_n, K=16; bf16 x bf16 -> fp32) with the accumulator in TMEM;
+//               (M = 128 or 64, N = block_n, K = 16; bf16 x bf16 -> fp32) with the accumulator in TMEM;
 //               tcgen05.commit releases smem stages / publishes the accumulator;
-//   * warps 2-5: epilogue    - tcgen05.ld 32x32b (lane = batch row, column = output feature), so
-//               the vocab arg-max is a thread-local scan; two TMEM accumulators let the epilogue
-//               of tile i overlap the main loop of tile i+1.
+//   * warps 2-5: epilogue    - tcgen05.ld 32x32b (lane = batch row, column = output feature), so the vocab arg-max
+//               is a thread-local scan; the load of the next 16 columns is in flight while the current ones are
+//               converted / compared / stored; two TMEM accumulators let the epilogue of tile i overlap the main
+//               loop of tile i+1.
 //   * batch rows are the UMMA M dimension (lanes), features the N dimension: rows >= M are never
 //     fetched (TMA box covers box_m rows only) and cost no HBM traffic.
 //   * block_n is chosen per problem so that the tile count is a near multiple of the SM count
@@ -22,6 +26,8 @@
 //   * bf16 results are rounded once from the fp32 accumulator, like the reference's cuBLAS GEMM;
 //     the arg-max compares the bf16-rounded logits and keeps the lowest index on ties
 //     (torch.argmax), across CTAs through a packed 64-bit atomicMax.
+//   * every launch can record a device-side trace (entry, dependency resolved, first / last operand bytes
+//     landed, first / last CTA exit) - ab200_set_trace_buffer - which is how ramp / stream / tail are told apart.
 //
 // The f32 parity mode (1e-5) uses a plain SIMT FFMA GEMM (exact fp32, no TF32) + row arg-max.
 #include <cuda.h>
