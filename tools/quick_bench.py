@@ -1,4 +1,4 @@
-"""Dev: device time per proposal (graph replay) at cfg2 / other batch sizes; env knobs AB200_PDL, AB200_L2_PREFETCH_KB."""
+"""Dev: device time per proposal (graph replay) at cfg2 / other batch sizes; release library, compiled-in launch parameters."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -22,4 +22,4 @@ for B in batches:
         for _ in range(200): model.generate_proposals(ids, hid, S)
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 200)
-    print(f"PDL={os.environ.get('AB200_PDL','1')} L2KB={os.environ.get('AB200_L2_PREFETCH_KB','dflt')} B={B}: {best*1e3:.1f} us/proposal -> {B*S/best*1e3:.0f} tok/s  tokens[0]={out[0].tolist()}", flush=True)
+    print(f"B={B}: {best*1e3:.1f} us/proposal -> {B*S/best*1e3:.0f} tok/s  tokens[0]={out[0].tolist()}", flush=True)
