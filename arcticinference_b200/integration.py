@@ -8,9 +8,9 @@ time the way the reference itself patches vLLM).
   (arctic_inference/vllm/spec_dec/arctic_speculator.py:753-866) is routed through the native draft loop for the
   configuration the hot path is built for (``method == "sum_lstm"``, ``tp_size == 1``, bf16 / fp32, CUDA); every other
   configuration keeps running the reference's own code - that is the reference's path, not a fallback of ours.
-  The native twin shares nothing but values with the module: it is (re)built from ``named_parameters()`` on first
-  use and whenever ``load_weights`` ran again; ``module.qhead is None`` (the oracle recipe) disables the FP8 head
-  on the twin as well.
+  The native twin SHARES the module's parameter storage (``share_parameters``: no second copy of the weights; only the
+  FP8 copy of the head is its own) and is rebuilt when the parameters move or ``load_weights`` ran again;
+  ``module.qhead is None`` (the oracle recipe) disables the FP8 head on the twin as well.
 
 Nothing here is needed by the native classes themselves; nothing here imports ``oracle/``.
 """
@@ -48,10 +48,12 @@ def _native_twin(module) -> "object":
                   inner_dim=module.inner_dim[-1], n_predict=module.n_predict,
                   num_lookahead_tokens=module.max_speculative_tokens,
                   max_num_seqs=getattr(module, "cuda_graph_max_batch_size", 256), dtype=p0.dtype, device=p0.device,
-                  scale_input=module.scale_input, enforce_eager=not getattr(module, "cuda_graph_mode", True))
-    twin.load_weights((k, v.data) for k, v in params.items())      # same names / shapes; qhead.* is rebuilt from head.*
-    if getattr(module, "qhead", None) is None:
-        twin.qhead = None
+                  scale_input=module.scale_input, enforce_eager=not getattr(module, "cuda_graph_mode", True),
+                  quantize_lm_head=None if getattr(module, "qhead", None) is not None else False,
+                  allocate_parameters=False)
+    # same names / shapes as the reference registers them (head rows = vocab padded to 64): shared, not copied;
+    # qhead.* is rebuilt from head.*
+    twin.share_parameters((k, v.data) for k, v in params.items() if not k.startswith("qhead"))
     module._b200_impl, module._b200_stamp = twin, stamp
     return twin
 

@@ -62,7 +62,7 @@ class ArcticLSTMSpeculator:
                  scale_input: bool = True, enforce_eager: bool = False,
                  emulate_eager_rounding: bool | int = True, alpha_flavor: str = "cuda",
                  quantize_lm_head: Optional[bool] = None, fp8_head_max_batch: int = 32,
-                 tp_size: int = 1, tp_rank: int = 0, tp_group=None) -> None:
+                 tp_size: int = 1, tp_rank: int = 0, tp_group=None, allocate_parameters: bool = True) -> None:
         self._lib = _capi.lib()  # fail loudly if the native library is missing
         # path A goes through the additive torch ops (arctic_inference::sum_lstm_cell, ::lm_head_argmax,
         # ::lstm_speculator_propose, ... - py_custom_ops.py), which call the C ABI
@@ -131,7 +131,13 @@ class ArcticLSTMSpeculator:
             raise ValueError("padded vocab size must be divisible by tp_size")
         self.vocab_padded = Vp
         self.vocab_per_rank = Vp // tp_size          # num_embeddings_per_partition
-        mk = lambda *shape: torch.zeros(*shape, dtype=dtype, device=self.device)
+        # allocate_parameters=False: zero-size placeholders of the right rank; share_parameters() adopts the
+        # caller's tensors (a drop-in next to the reference module must not hold a second copy of the weights)
+        mk = (lambda *shape: torch.zeros(*shape, dtype=dtype, device=self.device)) if allocate_parameters else \
+            (lambda *shape: torch.zeros(*([0] * len(shape)), dtype=dtype, device=self.device))
+        self._param_shapes = {"head.0.weight": (self.vocab_per_rank, D), "forget_emb.0.weight": (V, D),
+                              "projs.0.weight": (4 * D, H), "projs.1.weight": (4 * D, D), "cell_ln.0.weight": (D,),
+                              "cell_ln.0.bias": (D,), "state_ln.0.weight": (D,), "state_ln.0.bias": (D,)}
         self._params: Dict[str, torch.Tensor] = collections.OrderedDict([
             ("head.0.weight", mk(self.vocab_per_rank, D)),
             ("forget_emb.0.weight", mk(V, D)),
@@ -191,8 +197,43 @@ class ArcticLSTMSpeculator:
             else batch_size
         return self._head_q is not None and b <= self.fp8_head_max_batch
 
+    def share_parameters(self, named_tensors: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        """Adopt the caller's tensors as this model's parameters WITHOUT copying (same names as ``load_weights``
+        after gate fusing: ``head.0.weight [V_pad64, D]``, ``forget_emb.0.weight``, ``projs.{0,1}.weight``, the four
+        LayerNorm vectors).  A tensor is shared when it already has the exact shape, dtype, device, a dense row-major
+        layout and 16-byte alignment; anything else is copied like ``load_weights`` would.  Later in-place updates
+        of a shared tensor are seen by the bf16 path at once; call ``requantize()`` (or ``load_weights``) afterwards
+        to refresh the FP8 copy of the head.  Returns the names that were shared."""
+        shared = []
+        for name, t in named_tensors:
+            name = name.replace("speculator.", "")
+            if name not in self._params:
+                continue
+            ok = (tuple(t.shape) == tuple(self._param_shapes[name]) and t.dtype == self.dtype and t.device == self.device
+                  and t.is_contiguous() and t.data_ptr() % 16 == 0)
+            if ok:
+                self._params[name] = t.detach()
+                shared.append(name)
+            else:
+                if self._params[name].numel() == 0:
+                    self._params[name] = torch.zeros(*self._param_shapes[name], dtype=self.dtype, device=self.device)
+                self._set_param(name, t.to(device=self.device, dtype=self.dtype))
+        missing = [n for n, p in self._params.items() if p.numel() == 0]
+        if missing:
+            raise ValueError(f"share_parameters: no tensor given for {missing}")
+        self._invalidate_graphs()
+        self.requantize()
+        return shared
+
+    def requantize(self) -> None:
+        """Refresh the FP8 copy of the head from ``head.0.weight`` (in place: captured graphs stay valid)."""
+        if self.quantize_lm_head and self._head_q is not None:
+            self._quantize_head()
+
     def _set_param(self, name: str, value: torch.Tensor) -> None:
         p = self._params[name]
+        if p.numel() == 0 and name in getattr(self, "_param_shapes", {}):      # allocate_parameters=False: allocate on demand
+            p = self._params[name] = torch.zeros(*self._param_shapes[name], dtype=self.dtype, device=self.device)
         if name.startswith("head") and self.tp_size > 1 and value.shape[0] != p.shape[0]:
             # full (unsharded) head given: keep this rank's vocab partition
             lo = self.tp_rank * self.vocab_per_rank

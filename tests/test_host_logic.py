@@ -91,3 +91,24 @@ def test_lstm_parameter_layout_and_tp_partition():
     m.load_weights(list(parts.items()) + [("input_emb.0.weight", torch.zeros(1))])
     w = dict(m.named_parameters())["projs.1.weight"].float()
     assert [w[i * 32, 0].item() for i in range(4)] == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_share_parameters_adopts_storage_without_copying():
+    """The drop-in twin next to the reference module must not hold a second copy of the weights."""
+    from arcticinference_b200.speculator import ArcticLSTMSpeculator
+    m = ArcticLSTMSpeculator(vocab_size=1000, input_hidden_dim=48, inner_dim=32, n_predict=3, device="cpu",
+                             allocate_parameters=False)
+    assert all(p.numel() == 0 for _, p in m.named_parameters())
+    ts = {"head.0.weight": torch.randn(1024, 32).bfloat16(), "forget_emb.0.weight": torch.randn(1000, 32).bfloat16(),
+          "projs.0.weight": torch.randn(128, 48).bfloat16(), "projs.1.weight": torch.randn(128, 32).bfloat16(),
+          "cell_ln.0.weight": torch.randn(32).bfloat16(), "cell_ln.0.bias": torch.randn(32).bfloat16(),
+          "state_ln.0.weight": torch.randn(32).bfloat16(), "state_ln.0.bias": torch.randn(64).bfloat16()[::2]}   # strided
+    shared = m.share_parameters(ts.items())
+    p = dict(m.named_parameters())
+    assert "head.0.weight" in shared and p["head.0.weight"].data_ptr() == ts["head.0.weight"].data_ptr()
+    assert "state_ln.0.bias" not in shared and torch.equal(p["state_ln.0.bias"], ts["state_ln.0.bias"])     # copied
+    ts["projs.1.weight"].zero_()
+    assert not p["projs.1.weight"].any()                                  # later in-place updates are visible
+    with pytest.raises(ValueError, match="no tensor given"):
+        ArcticLSTMSpeculator(vocab_size=1000, input_hidden_dim=48, inner_dim=32, n_predict=3, device="cpu",
+                             allocate_parameters=False).share_parameters([("head.0.weight", ts["head.0.weight"])])

@@ -103,6 +103,8 @@ def test_one_call_drop_in_patches_the_reference_class(spec):
             after = ref.generate_proposals(ids, hid, S)
             twin = ref._b200_impl
             assert twin.qhead is None                                                 # ref.qhead is None -> bf16 head
+            for k, p in ref.named_parameters():                                       # storage shared, not copied
+                assert dict(twin.named_parameters())[k].data_ptr() == p.data_ptr(), k
             assert torch.equal(after, twin.generate_proposals(ids, hid, S))
             assert (after == before).float().mean().item() >= 0.999
             with pytest.raises(ValueError, match="Max speculative tokens"):           # same error contract
