@@ -169,3 +169,27 @@ def test_class_is_routed_through_the_ops(ops, monkeypatch):
     names = " ".join(seen)
     for op in ("lstm_speculator_propose", "speculator_rms_scale", "speculator_linear", "sum_lstm_cell", "lm_head_argmax"):
         assert f"arctic_inference.{op}" in names, (op, seen)
+
+
+def test_ops_trace_under_torch_compile_fullgraph(ops):
+    """SURVEY 8b row 4 / VERDICT r1 missing #3: the ops must be visible to torch.compile consumers.  Dynamo traces a
+    function that mixes ATen ops with ours into ONE graph (fullgraph=True needs the registered fake kernels); the
+    "eager" backend then runs the captured graph, i.e. our kernels - no inductor code generation is involved."""
+    import torch._dynamo
+    V, D, B = 4096, 256, 8
+    w = O.make_weights(V, D, D, torch.bfloat16, seed=0, device=DEV)
+
+    def step(x, tok, cprev):
+        gates = ops.speculator_linear(x * 1.0, w["projs.1.weight"])
+        state, cell = ops.sum_lstm_cell(gates, w["forget_emb.0.weight"], tok, cprev, w["cell_ln.0.weight"],
+                                        w["cell_ln.0.bias"], w["state_ln.0.weight"], w["state_ln.0.bias"], 23.0, 1e-6, 1)
+        return ops.lm_head_argmax(state, w["head.0.weight"], V) + 0, cell
+
+    x = torch.randn(B, D, device=DEV).to(torch.bfloat16)
+    tok = torch.randint(0, V, (B,), device=DEV)
+    cprev = torch.zeros(B, D, device=DEV, dtype=torch.bfloat16)
+    want_tok, want_cell = step(x, tok, cprev)
+    torch._dynamo.reset()
+    compiled = torch.compile(step, backend="eager", fullgraph=True)
+    got_tok, got_cell = compiled(x, tok, cprev)
+    assert torch.equal(got_tok, want_tok) and torch.equal(got_cell.view(torch.int16), want_cell.view(torch.int16))
