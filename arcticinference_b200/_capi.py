@@ -116,6 +116,7 @@ DEBUG_SIGNATURES = {
                                          c_int64, c_void_p]),
     "ab200_debug_mlp_generic": (c_int32, [c_int32]),
     "ab200_debug_set_tunable": (c_int32, [c_char_p, c_int32]),
+    "ab200_debug_max_clusters_of_4": (c_int32, []),
 }
 
 _lib = None

@@ -64,6 +64,8 @@ struct Tune {
   int pre_stages = -1;     // smem stages filled with W before the dependency wait (-1 = all)
   int l2_prefetch_kb = 0;  // arg-max GEMM: extra W pipeline steps prefetched into L2 before the dependency wait
   int gate_l2_prefetch = 0; // store-epilogue GEMM: the same
+  int gemm_4cta = 0;        // > 128 rows: clusters of two CTA pairs sharing the activation tile by TMA multicast
+  int dbg_skip = 0;         // debug flavour only: CTA-pair kernel leaves operand loads out (timing experiments)
   int gate_block_n = 0;    // debug: force the tile width of the store-epilogue GEMM (0 = heuristic)
   int head_block_n = 0;    // debug: force the tile width of the arg-max GEMM
   int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)

@@ -203,6 +203,9 @@ struct GemmParams {
   int32_t num_k_blocks;
   int32_t stages;
   int32_t l2_prefetch_kb;  // extra W k-blocks prefetched into L2 before the dependency wait
+#ifdef AB200_DEBUG
+  int32_t dbg_skip;        // 2cta kernel, timing experiments only: bit 0 = no x loads, bit 1 = no W loads after the ring fill
+#endif
   int32_t pre_stages;      // smem stages filled with W before the dependency wait
   int32_t late_trigger;    // 1: griddepcontrol.launch_dependents after the last TMA load
   int32_t m64;             // 1: UMMA M = 64 (MT == 1, <= 64 rows): row r lives in TMEM lane (r/16)*32 + r%16
@@ -584,6 +587,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* desc, 
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// the same load, delivered to the same shared-memory offset of every CTA in `mask` (cluster ranks); the bytes are
+// counted on the stage barrier of EACH destination's pair leader (peer bit cleared in every destination)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
+                                                   int32_t c1, uint16_t mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
                : "memory");
@@ -601,26 +614,34 @@ __device__ __forceinline__ void umma_2sm_bf16(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  const uint16_t mask = 3;
+// arrive (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"(mask)
       : "memory");
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                   const GemmParams p) {
+// CL = 2: one CTA pair per cluster.  CL = 4: TWO pairs per cluster work on ADJACENT weight tiles and share the
+// activation k-blocks: every CTA fetches half of the 128 rows it needs and multicasts them to its counterpart in the
+// other pair, so the x bytes crossing L2 -> SM halve.  (Measured, profiles/r2_gemm_tune.md section 6: at 256 rows
+// the pair kernel is bound by the L2 -> SM fabric - 2.05 GB per head launch at ~8.8 TB/s, half of it x re-reads -
+// neither by HBM (167 us) nor by the tensor pipe (145 us).)  A stage is released only when BOTH pairs have consumed
+// it (their commits arrive on the stage-empty barrier of all four CTAs), since both pairs' producers write into it.
+template <int EPI, int CL>
+__device__ __forceinline__ void gemm_pair_body(const CUtensorMap& tmap_x, const CUtensorMap& tmap_w,
+                                               const GemmParams& p) {
   constexpr int kAcc = 256;   // TMEM columns per accumulator buffer (block_n <= 256), two buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = static_cast<int>(blockIdx.x >> 1), npairs = static_cast<int>(gridDim.x >> 1);
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;                           // rank inside the MMA pair
+  const int sub = CL == 4 ? static_cast<int>(crank >> 1) : 0; // which pair of the cluster
+  // `pair` / `npairs`: index and number of the units that own weight tiles round-robin (CL = 4: clusters)
+  const int pair = static_cast<int>(blockIdx.x) / CL, npairs = static_cast<int>(gridDim.x) / CL;
+  auto tile_of = [&](int round) { return CL == 4 ? 2 * (pair + round * npairs) + sub : pair + round * npairs; };
   const int stages = p.stages;
   const int half_n = p.block_n >> 1;
   const uint32_t b_bytes = static_cast<uint32_t>(half_n) * 128u;
@@ -642,7 +663,7 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), 1);
+        mbar_init(empty_bar(s), CL / 2);   // one commit per pair that reads (and whose producers refill) the stage
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
@@ -663,7 +684,10 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   if (!p.late_trigger) pdl_launch_dependents();
 
   const int num_kb = p.num_k_blocks;
-  const int my_tiles = pair < p.num_n_tiles ? (p.num_n_tiles - 1 - pair) / npairs + 1 : 0;
+  // CL = 4: the unit owns tile PAIRS (an odd tile count leaves the last partner out of bounds: zero-filled by TMA,
+  // masked by n_valid in the epilogue) - both pairs of a cluster must run the same number of pipeline steps
+  const int units_of_work = CL == 4 ? (p.num_n_tiles + 1) / 2 : p.num_n_tiles;
+  const int my_tiles = pair < units_of_work ? (units_of_work - 1 - pair) / npairs + 1 : 0;
   // Batches of 257..512 rows: every weight tile is used for MH = 2 m-blocks of 256 rows back to back (work item =
   // (tile, m-block), m-block fastest), each into its own TMEM accumulator buffer - ONE launch and one pass over
   // the tile list instead of two launches that each stream all the weights (the second read of a tile comes from
@@ -674,10 +698,18 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       const int total = my_items * num_kb;
-      auto n0_of = [&](int g) { return (pair + ((g / num_kb) / MH) * npairs) * p.block_n + static_cast<int>(rank) * half_n; };
+      auto n0_of = [&](int g) { return tile_of((g / num_kb) / MH) * p.block_n + static_cast<int>(rank) * half_n; };
       auto load_x = [&](int g, int stage) {
-        tma_load_2d_2sm(smem_base + stage * stage_bytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK,
-                        ((g / num_kb) % MH) * 2 * kTileM + static_cast<int>(rank) * kTileM, kEvictLast);
+        const int row0 = ((g / num_kb) % MH) * 2 * kTileM + static_cast<int>(rank) * kTileM;
+        if constexpr (CL == 4) {
+          // rows [sub*64, sub*64 + 64) of this CTA's 128, to both CTAs of the cluster with this pair rank
+          tma_load_2d_2sm_mc(smem_base + stage * stage_bytes + sub * (kABytes / 2), &tmap_x, full_bar(stage),
+                             (g % num_kb) * kBlockK, row0 + sub * (kTileM / 2),
+                             static_cast<uint16_t>((1u << rank) | (4u << rank)), kEvictLast);
+        } else {
+          tma_load_2d_2sm(smem_base + stage * stage_bytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK, row0,
+                          kEvictLast);
+        }
       };
       auto load_w = [&](int g, int stage) {
         tma_load_2d_2sm(smem_base + stage * stage_bytes + kABytes, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK,
@@ -695,9 +727,18 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       uint32_t phase = pre == stages ? 1u : 0u;
       for (int g = pre; g < total; ++g) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
+#ifdef AB200_DEBUG
+        // bound-finding experiment (WRONG results, timing only): leave operand loads out after the first ring fill
+        const uint32_t skip = static_cast<uint32_t>(p.dbg_skip);
+        const uint32_t tx = p.tx_bytes - ((skip & 1u) ? 2u * kABytes : 0u) - ((skip & 2u) ? 2u * b_bytes : 0u);
+        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx);
+        if (!(skip & 1u)) load_x(g, stage);
+        if (!(skip & 2u)) load_w(g, stage);
+#else
         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
         load_x(g, stage);
         load_w(g, stage);
+#endif
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
       if (p.late_trigger) pdl_launch_dependents();
@@ -727,8 +768,8 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_2sm_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(empty_bar(stage));
-            if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
+            umma_commit_2sm(empty_bar(stage), CL == 4 ? 0xF : 0x3);
+            if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc), static_cast<uint16_t>(0x3u << (2 * sub)));
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -745,7 +786,7 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int mhi = it % MH;
-      const int n0 = (pair + (it / MH) * npairs) * p.block_n;
+      const int n0 = tile_of(it / MH) * p.block_n;
       const int row = mhi * 2 * kTileM + row_in_block;                     // batch row of this thread
       const bool row_ok = row < p.m_rows;
       const bool warp_has_rows = mhi * 2 * kTileM + static_cast<int>(rank) * kTileM + quad * 32 < p.m_rows;
@@ -849,6 +890,26 @@ gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     trace_stamp(p.trace, 5);
   }
 }
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn_sm100_2cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const GemmParams p) {
+  gemm_pair_body<EPI, 2>(tmap_x, tmap_w, p);
+}
+
+#ifdef AB200_DEBUG
+// Two CTA pairs per cluster sharing the activation tile by TMA multicast (tmap_x box = 64 rows).  DEBUG flavour only:
+// bit-identical to the pair kernel and ~12 % faster per SM, but a B200 co-schedules only 33 clusters of 4 (132 of
+// its 148 SMs - GPC sizes are not multiples of 4), which cancels the gain (tools/cl4_probe.py,
+// profiles/r2_gemm_tune.md section 6).
+template <int EPI>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn_sm100_4cta(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const GemmParams p) {
+  gemm_pair_body<EPI, 4>(tmap_x, tmap_w, p);
+}
+#endif
 
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1065,6 +1126,31 @@ static int launch_gemm_pass(const void* x, const void* w, int64_t m_rows, int64_
 }
 
 
+#ifdef AB200_DEBUG
+// How many 4-CTA clusters of the pair kernel the device can run at once (one CTA per SM): asked once per device.
+template <int EPI>
+static int max_clusters_of_4() {
+  static std::atomic<int> cached[kMaxDevices];   // 0 = not asked yet, -1 = none
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  int v = cached[dev].load(std::memory_order_acquire);
+  if (v != 0) return v < 0 ? 0 : v;
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (ensure_max_smem(gemm_tn_sm100_4cta<EPI>, attr_set, kSmemLimit) != AB200_OK) return 0;
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(4 * 64);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kSmemLimit;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tn_sm100_4cta<EPI>, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    n = 0;
+  }
+  cached[dev].store(n > 0 ? n : -1, std::memory_order_release);
+  return n;
+}
+#endif
+
 // 129..256 rows: the CTA-pair kernel (see gemm_tn_sm100_2cta)
 template <int EPI>
 static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, int64_t w_rows, int64_t K,
@@ -1074,12 +1160,22 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   static std::atomic<bool> attr_set[kMaxDevices];
   int rc = ensure_max_smem(gemm_tn_sm100_2cta<EPI>, attr_set, kSmemLimit);
   if (rc != AB200_OK) return rc;
-  const int pairs = sm_count() / 2;
+#ifdef AB200_DEBUG
+  // experiment: 4-CTA clusters (two pairs sharing the activation tile by multicast), as many as the device
+  // co-schedules
+  const int clusters4 = tune().gemm_4cta ? max_clusters_of_4<EPI>() : 0;
+  const bool cl4 = clusters4 * 4 >= sm_count() * 7 / 8;
+#else
+  constexpr int clusters4 = 0;
+  constexpr bool cl4 = false;
+#endif
+  const int pairs = cl4 ? clusters4 : sm_count() / 2;   // units that own weight tiles (cl4: tile PAIRS)
   // tile width: multiple of 32 (each CTA holds half of it), balanced over the CTA pairs
   int bn = 32;
   double best_cost = 1e30;
   for (int c = 32; c <= 256; c += 32) {
-    const int64_t tiles = (n_valid + c - 1) / c;
+    int64_t tiles = (n_valid + c - 1) / c;
+    if (cl4) tiles = (tiles + 1) / 2;
     const int64_t waves = (tiles + pairs - 1) / pairs;
     const double cost = static_cast<double>(waves) * (c + 16.0);
     if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && c > bn)) {
@@ -1095,7 +1191,7 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   if (stages > kMaxStages) stages = kMaxStages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
   CUtensorMap tmx, tmw;
-  rc = get_tmap(&tmx, x, m_rows, K, ldx, kTileM, 2);
+  rc = get_tmap(&tmx, x, m_rows, K, ldx, cl4 ? kTileM / 2 : kTileM, 2);
   if (rc != AB200_OK) return rc;
   rc = get_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2);
   if (rc != AB200_OK) return rc;
@@ -1107,6 +1203,9 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
   p.stages = stages;
   p.l2_prefetch_kb = 0;
+#ifdef AB200_DEBUG
+  p.dbg_skip = tune().dbg_skip;
+#endif
   p.late_trigger = gemm_late_trigger();
   p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
@@ -1126,8 +1225,18 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.tokens_stride = ax.tokens_stride;
   p.done_counter = ax.done_counter;
   p.trace = next_trace_slot();
-  const int use_pairs = num_n_tiles < pairs ? num_n_tiles : pairs;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 + 256;
+#ifdef AB200_DEBUG
+  if (cl4) {
+    const int work = (num_n_tiles + 1) / 2;
+    const int use = work < pairs ? work : pairs;
+    LaunchCfg cfg(dim3(4 * use), dim3(kGemmThreads), smem, s);
+    AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_tn_sm100_4cta<EPI>, tmx, tmw, p));
+    AB200_CHECK_LAUNCH("gemm_tn_sm100_4cta");
+    return AB200_OK;
+  }
+#endif
+  const int use_pairs = num_n_tiles < pairs ? num_n_tiles : pairs;
   LaunchCfg cfg(dim3(2 * use_pairs), dim3(kGemmThreads), smem, s);
   AB200_CUDA_OK(cudaLaunchKernelEx(&cfg.cfg, gemm_tn_sm100_2cta<EPI>, tmx, tmw, p));
   AB200_CHECK_LAUNCH("gemm_tn_sm100_2cta");
@@ -1195,9 +1304,19 @@ int init_gemm_kernels() {
   AB200_INIT_ATTR(gemm_tn_sm100<EPI_ARGMAX, 1, KIND_FP8>);
   AB200_INIT_ATTR(gemm_tn_sm100_2cta<EPI_STORE>);
   AB200_INIT_ATTR(gemm_tn_sm100_2cta<EPI_ARGMAX>);
+#ifdef AB200_DEBUG
+  AB200_INIT_ATTR(gemm_tn_sm100_4cta<EPI_STORE>);
+  AB200_INIT_ATTR(gemm_tn_sm100_4cta<EPI_ARGMAX>);
+  (void)max_clusters_of_4<EPI_STORE>();    // occupancy asked here, outside any capture
+  (void)max_clusters_of_4<EPI_ARGMAX>();
+#endif
 #undef AB200_INIT_ATTR
   return AB200_OK;
 }
+
+#ifdef AB200_DEBUG
+extern "C" AB200_API int32_t ab200_debug_max_clusters_of_4(void) { return max_clusters_of_4<EPI_ARGMAX>(); }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // exact-fp32 SIMT GEMM (parity mode) : out[M,N] = x[M,K] . w[N,K]^T

@@ -141,7 +141,7 @@ extern "C" int32_t ab200_debug_set_tunable(const char* name, int32_t value) {
   struct { const char* n; int* p; } tab[] = {
       {"pdl", &t.pdl}, {"umma_m64", &t.umma_m64}, {"gemm_2cta", &t.gemm_2cta},
       {"rows_per_pass", &t.rows_per_pass}, {"late_trigger", &t.late_trigger},
-      {"pre_stages", &t.pre_stages}, {"l2_prefetch_kb", &t.l2_prefetch_kb}, {"gate_l2_prefetch", &t.gate_l2_prefetch},
+      {"pre_stages", &t.pre_stages}, {"l2_prefetch_kb", &t.l2_prefetch_kb}, {"gate_l2_prefetch", &t.gate_l2_prefetch}, {"gemm_4cta", &t.gemm_4cta}, {"dbg_skip", &t.dbg_skip},
       {"gate_block_n", &t.gate_block_n}, {"head_block_n", &t.head_block_n},
       {"max_stages", &t.max_stages}, {"gate_mh2", &t.gate_mh2}, {"gate_kbs", &t.gate_kbs}, {"head_kbs", &t.head_kbs}};
   for (auto& e : tab)

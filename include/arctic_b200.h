@@ -319,6 +319,8 @@ AB200_API int32_t ab200_debug_mlp_generic(int32_t on);
  * "late_trigger", "pre_stages", "l2_prefetch_kb", "gate_block_n", "head_block_n", "max_stages", ...
  * The release library compiles the defaults in and reads no environment variable. */
 AB200_API int32_t ab200_debug_set_tunable(const char* name, int32_t value);
+/* how many 4-CTA clusters of the pair GEMM the current device co-schedules (cudaOccupancyMaxActiveClusters) */
+AB200_API int32_t ab200_debug_max_clusters_of_4(void);
 #endif /* AB200_DEBUG */
 
 /* Whole draft loop: ln0 -> S x (gate GEMM -> fused cell -> head GEMM + argmax) -> token unpack.

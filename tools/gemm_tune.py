@@ -100,6 +100,14 @@ if what in ("pair",):
         rows.append(run_case(M, N, K, False, warm_x=True, **DEFAULTS))
         for bn in (96, 128, 192, 256):
             rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "gate_block_n": bn}))
+if what in ("bound",):
+    # what bounds the CTA-pair kernel: the same launches with the x loads (1), the W loads (2) or both (3) left out
+    # after the first ring fill (debug flavour only; results are garbage, the timing is the point)
+    for (M, N, K, head) in ((256, 128256, 4096, True), (256, 16384, 4096, False), (512, 16384, 4096, False),
+                            (512, 11520, 2880, False)):
+        for skip in (0, 1, 2, 3):
+            rows.append(run_case(M, N, K, head, warm_x=True, **{**DEFAULTS, "dbg_skip": skip}))
+    tune(dbg_skip=0)
 if what in ("head", "all"):
     for kbs in (1, 2):
         rows.append(run_case(64, 128256, 4096, True, warm_x=True, **{**DEFAULTS, "head_kbs": kbs}))
