@@ -531,21 +531,44 @@ def bench_cell_hbm_regime(dev, peak_gbs: float, rows: int = 16384, D: int = 4096
     out = {"rows": rows, "D": D, "algorithmic_bytes": nbytes,
            "note": "bf16; exact = bit-identical to eager PyTorch (every ATen rounding point); faithful = same "
                    "rounding points, unguarded fast sigmoid/GELU (emulate_eager_rounding=2)"}
+    def launch(mode, n_rows, r0=0):
+        _capi.check(lib.ab200_sum_lstm_cell(
+            gates[r0:].data_ptr(), 4 * D, emb.data_ptr(), toks[r0:].data_ptr(), None, cprev[r0:].data_ptr(),
+            ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr(), state[r0:].data_ptr(),
+            cell[r0:].data_ptr(), n_rows, D, V, 23.07, 1e-6, _capi.AB200_BF16, mode, None, None, None, None, st), "cell")
+
     for name, mode in (("exact", 1), ("faithful", 2)):
         ts = []
         for _ in range(iters + 2):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _capi.check(lib.ab200_sum_lstm_cell(
-                gates.data_ptr(), 4 * D, emb.data_ptr(), toks.data_ptr(), None, cprev.data_ptr(), ln[0].data_ptr(),
-                ln[1].data_ptr(), ln[2].data_ptr(), ln[3].data_ptr(), state.data_ptr(), cell.data_ptr(), rows, D, V,
-                23.07, 1e-6, _capi.AB200_BF16, mode, None, None, None, None, st), "cell")
+            launch(mode, rows)
             e1.record()
             torch.cuda.synchronize(dev)
             ts.append(e0.elapsed_time(e1))
         ms = statistics.median(ts[2:] or ts)
         out[name] = {"ms": ms, "gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak_gbs}
+    # 4 096 rows: 268 MB per launch, more than twice the L2, so launches run back to back between
+    # ONE event pair instead of one flushed launch per pair - a 50-us kernel is otherwise charged the ~5 us of
+    # event-to-kernel gaps of a lone launch
+    small = 4096
+    if rows >= small:
+        nb_small = small * D * 2 * 8 + 4 * D * 2 + 8 * small
+        launch(1, small)
+        torch.cuda.synchronize(dev)
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            launch(1, small, (i % (rows // small)) * small)     # a different quarter of the 1 GB working set each time
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        out["rows_4096_exact"] = {"ms": ms, "gbs": nb_small / ms / 1e6, "frac_of_hbm_peak": nb_small / ms / 1e6 / peak_gbs,
+                                  "algorithmic_bytes": nb_small,
+                                  "how": f"{reps} back-to-back launches between one event pair, rotating over the "
+                                         f"{rows // small} quarters of the {rows}-row buffers (never L2-resident)"}
     return out
 
 

@@ -147,6 +147,55 @@ def test_bf16x2_kernel_bit_identical_to_generic_kernel(capi, B, D, gate_std, wit
         assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), "fp8 state copy differs"
 
 
+@pytest.mark.parametrize("B,D,gate_std,with_prev", [
+    (2048, 1024, 1.3, True), (2304, 4096, 1.3, True), (2100, 4096, 1.3, False), (2051, 2880, 1.0, True),
+    (4099, 512, 2.0, True), (9000, 4096, 1.3, True), (2049, 40, 1.0, True),
+])
+def test_large_batch_cell_bit_identical(capi, B, D, gate_std, with_prev):
+    """Thousands of rows (the kernel's HBM-bound regime, 16 elements per thread from 4096 rows on), without the FP8
+    state copy: bit-identical to the generic kernel, to the same rows launched in chunks of 1000, in both rounding
+    modes, with out-of-range token ids clamped, and with the cell state updated in place."""
+    torch.manual_seed(B * 7 + D)
+    V = 5000
+    gates = (torch.randn(B, 4 * D, device=DEV) * gate_std).to(torch.bfloat16)
+    emb = (torch.randn(V, D, device=DEV) * 0.02).to(torch.bfloat16)
+    tok = torch.randint(0, V, (B,), device=DEV)
+    tok[0], tok[1] = -5, V + 3                       # out-of-range ids are clamped, as in the row kernel
+    cprev = (torch.randn(B, D, device=DEV) * 0.8).to(torch.bfloat16) if with_prev else None
+    ln = [(torch.randn(D, device=DEV) * 0.1 + (1.0 if i % 2 == 0 else 0.0)).to(torch.bfloat16) for i in range(4)]
+    alpha = 23.07
+    a = run_cell(capi, False, gates, emb, tok, cprev, ln, alpha)
+    b = run_cell(capi, True, gates, emb, tok, cprev, ln, alpha)
+    assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16)), "state differs from the generic kernel"
+    assert torch.equal(a[1].view(torch.int16), b[1].view(torch.int16)), "cell differs from the generic kernel"
+    lib = capi.lib()
+
+    def call(mode, rows0, rows1, state, cell, cp):
+        n = rows1 - rows0
+        capi.check(lib.ab200_sum_lstm_cell(
+            gates[rows0:].data_ptr(), gates.stride(0), emb.data_ptr(), tok[rows0:].data_ptr(), None,
+            cp[rows0:].data_ptr() if cp is not None else None, ln[0].data_ptr(), ln[1].data_ptr(), ln[2].data_ptr(),
+            ln[3].data_ptr(), state[rows0:].data_ptr(), cell[rows0:].data_ptr(), n, D, V, alpha, 1e-6,
+            capi.AB200_BF16, mode, None, None, None, None, st()))
+
+    for mode in (1, 2):
+        s_big, c_big = torch.empty(B, D, device=DEV, dtype=torch.bfloat16), torch.empty(B, D, device=DEV, dtype=torch.bfloat16)
+        s_chk, c_chk = torch.empty_like(s_big), torch.empty_like(c_big)
+        call(mode, 0, B, s_big, c_big, cprev)                       # one launch
+        for r0 in range(0, B, 1000):                                # chunks (a different launch shape below 4096 rows)
+            call(mode, r0, min(B, r0 + 1000), s_chk, c_chk, cprev)
+        torch.cuda.synchronize()
+        assert torch.equal(s_big.view(torch.int16), s_chk.view(torch.int16)), f"mode {mode}: state"
+        assert torch.equal(c_big.view(torch.int16), c_chk.view(torch.int16)), f"mode {mode}: cell"
+    if cprev is not None:                                           # in place: cell_out aliases cell_prev
+        inplace = cprev.clone()
+        s2 = torch.empty(B, D, device=DEV, dtype=torch.bfloat16)
+        call(1, 0, B, s2, inplace, inplace)
+        torch.cuda.synchronize()
+        assert torch.equal(inplace.view(torch.int16), a[1].view(torch.int16))
+        assert torch.equal(s2.view(torch.int16), a[0].view(torch.int16))
+
+
 def test_bf16x2_kernel_adversarial_values(capi):
     """Gate pre-activations that hit every special region: huge, tiny, zero, negative zero, the
     GELU table range, values whose sigmoid / GELU sits next to a bf16 rounding tie."""
