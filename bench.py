@@ -40,6 +40,7 @@ port, all host threads) on the same config; rank 0 only.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -918,6 +919,20 @@ def bench_fp8_head(dev, model, steps, warmup):
     return res
 
 
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """fd-level: whatever C libraries write to stdout inside the block goes to stderr."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_ours(args):
     import torch
     from arcticinference_b200 import _capi, replicas
@@ -929,7 +944,12 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:
-        replicas.init_from_env("nccl", dev)
+        # NCCL prints its version banner on the C-level stdout when the communicator comes up: keep this process's
+        # stdout for the ONE JSON line (fd-level redirect to stderr around init + the first collective)
+        with _stdout_to_stderr():
+            replicas.init_from_env("nccl", dev)
+            replicas.barrier()
+            torch.cuda.synchronize(dev)
     V, H, D, S, B = (CFG[k] for k in "VHDSB")
     peak, peak_src = measured_peak_gbs()
 
