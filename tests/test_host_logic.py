@@ -112,3 +112,17 @@ def test_share_parameters_adopts_storage_without_copying():
     with pytest.raises(ValueError, match="no tensor given"):
         ArcticLSTMSpeculator(vocab_size=1000, input_hidden_dim=48, inner_dim=32, n_predict=3, device="cpu",
                              allocate_parameters=False).share_parameters([("head.0.weight", ts["head.0.weight"])])
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    """bench.py --impl reference under torchrun (N > 1): rank 0 alone runs and prints; every other rank exits 0 without
+    work and without a byte on stdout (the driver reads ONE JSON line per arm)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == ""
