@@ -126,3 +126,27 @@ def test_reference_arm_is_silent_on_other_ranks():
                         "--steps", "1", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == ""
+
+
+def test_sum_rnn_parameter_names_and_validation():
+    """ArcticSumRNNSpeculator registers exactly the parameter names / shapes of the reference's
+    ArcticLSTMSpeculator(method="sum_rnn") Sequential stacks (arctic_speculator.py:476-536) - compared with the oracle's
+    weight factory, which the goldens pin to the unmodified class - and rejects what the reference cannot run."""
+    from arcticinference_b200.sum_rnn_speculator import ArcticSumRNNSpeculator, parse_dims
+    from oracle import sum_rnn_ref as R
+    assert parse_dims("64.128") == [64, 128] and parse_dims(64) == [64] and parse_dims((8, 16)) == [8, 16]
+    for emb, proj, inner, tie in (("64.64", "64.64", "64.128", True), ("128.128.128", "128.128", "128.64.256", False),
+                                  ("64", "64", "64", True), ("64", "64.64", "64", False)):
+        m = ArcticSumRNNSpeculator(vocab_size=1000, input_hidden_dim=96, emb_dim=emb, proj_dim=proj, inner_dim=inner,
+                                   n_predict=3, tie_weights=tie, device="cpu", max_num_seqs=8)
+        w = R.make_sumrnn_weights(1000, 96, emb, proj, inner, 3, tie, torch.bfloat16)
+        assert {k: tuple(v.shape) for k, v in m.named_parameters()} == {k: tuple(v.shape) for k, v in w.items()}
+        m.load_weights(w.items())
+        got = dict(m.named_parameters())
+        assert all(torch.equal(got[k], w[k]) for k in w)
+    with pytest.raises(ValueError, match="must equal inner_dim"):
+        ArcticSumRNNSpeculator(vocab_size=1000, input_hidden_dim=96, emb_dim="64.96", proj_dim="64", inner_dim="64",
+                               n_predict=3, device="cpu")
+    with pytest.raises(ValueError, match="must equal inner_dim"):
+        ArcticSumRNNSpeculator(vocab_size=1000, input_hidden_dim=96, emb_dim="64", proj_dim="32", inner_dim="64",
+                               n_predict=3, device="cpu")
