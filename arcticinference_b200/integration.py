@@ -6,7 +6,8 @@ time the way the reference itself patches vLLM).
   signatures, same torch op schema, backed by ``ab200_kv_write_bulk``.
 * ``patch_lstm_speculator()`` - hot path A: ``ArcticLSTMSpeculator.generate_proposals``
   (arctic_inference/vllm/spec_dec/arctic_speculator.py:753-866) is routed through the native draft loop for the
-  configuration the hot path is built for (``method == "sum_lstm"``, ``tp_size == 1``, bf16 / fp32, CUDA); every other
+  configurations the native classes cover (``method == "sum_lstm"`` or ``"sum_rnn"`` - the latter with single or
+  stacked dims -, ``tp_size == 1``, bf16 / fp32, CUDA); every other
   configuration keeps running the reference's own code - that is the reference's path, not a fallback of ours.
   The native twin SHARES the module's parameter storage (``share_parameters``: no second copy of the weights; only the
   FP8 copy of the head is its own) and is rebuilt when the parameters move or ``load_weights`` ran again;
@@ -43,6 +44,20 @@ def _native_twin(module) -> "object":
     twin = getattr(module, "_b200_impl", None)
     if twin is not None and getattr(module, "_b200_stamp", None) == stamp:
         return twin
+    if getattr(module, "method", None) == "sum_rnn":
+        # :476-536, :693-704: dims are lists on the module; same parameter names, storage shared
+        from .sum_rnn_speculator import ArcticSumRNNSpeculator
+        p0 = params["proj.0.0.weight"]
+        twin = ArcticSumRNNSpeculator(
+            vocab_size=module.vocab_size, input_hidden_dim=module.input_hidden_dim, emb_dim=list(module.emb_dim),
+            proj_dim=list(module.proj_dim), inner_dim=list(module.inner_dim), n_predict=module.n_predict,
+            num_lookahead_tokens=module.max_speculative_tokens, tie_weights=module.tie_weights,
+            max_num_seqs=getattr(module, "cuda_graph_max_batch_size", 256), dtype=p0.dtype, device=p0.device,
+            scale_input=module.scale_input, enforce_eager=not getattr(module, "cuda_graph_mode", True),
+            quantize_lm_head=None if getattr(module, "qhead", None) is not None else False)
+        twin.share_parameters((k, v.data) for k, v in params.items() if not k.startswith("qhead"))
+        module._b200_impl, module._b200_stamp = twin, stamp
+        return twin
     p0 = params["projs.0.weight"]
     twin = Native(vocab_size=module.vocab_size, input_hidden_dim=module.input_hidden_dim,
                   inner_dim=module.inner_dim[-1], n_predict=module.n_predict,
@@ -70,7 +85,7 @@ def patch_lstm_speculator(cls=None):
     @functools.wraps(original)
     def generate_proposals(self, input_ids: torch.Tensor, previous_hidden_states: torch.Tensor,
                            num_predict_tokens: int):
-        if (getattr(self, "method", None) == "sum_lstm" and getattr(self, "tp_size", 1) == 1
+        if (getattr(self, "method", None) in ("sum_lstm", "sum_rnn") and getattr(self, "tp_size", 1) == 1
                 and previous_hidden_states.is_cuda and previous_hidden_states.dtype in (torch.bfloat16, torch.float32)):
             return _native_twin(self).generate_proposals(input_ids, previous_hidden_states, num_predict_tokens)
         return original(self, input_ids, previous_hidden_states, num_predict_tokens)

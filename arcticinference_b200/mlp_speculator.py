@@ -154,6 +154,31 @@ class ArcticMLPSpeculator:
         if self.quantize_lm_head:
             self._quantize_heads()
 
+    def share_parameters(self, named_tensors: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        """Adopt the caller's tensors as parameters WITHOUT copying where they already have the exact shape, dtype,
+        device, a dense layout and 16-byte alignment (anything else is copied like ``load_weights``); captured graphs
+        are dropped, the FP8 heads re-quantised in place.  Returns the names that were shared."""
+        shared, rest = [], []
+        for name, t in named_tensors:
+            name = name.replace("speculator.", "")
+            if name.startswith("qhead") or name not in self._params:
+                continue
+            p = self._params[name]
+            if (tuple(t.shape) == tuple(p.shape) and t.dtype == self.dtype and t.device == p.device
+                    and t.is_contiguous() and t.data_ptr() % 16 == 0):
+                self._params[name] = t.detach()
+                shared.append(name)
+            else:
+                rest.append((name, t))
+        self._desc = None
+        self.cuda_graphs.clear()
+        self._graph_epoch += 1
+        if rest:
+            self.load_weights(rest)
+        elif self.quantize_lm_head:
+            self._quantize_heads()
+        return shared
+
     def _quantize_heads(self) -> None:
         """IN PLACE into the buffers allocated at construction: graphs captured before a second
         load_weights() keep reading valid, freshly quantised heads."""

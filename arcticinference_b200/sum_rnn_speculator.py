@@ -192,6 +192,35 @@ class ArcticSumRNNSpeculator:
             p.copy_(w)
         self.cuda_graphs.clear()
 
+    def share_parameters(self, named_tensors: Iterable[Tuple[str, torch.Tensor]]) -> List[str]:
+        """Adopt the caller's tensors (the reference's parameter names) WITHOUT copying where shape, dtype, device,
+        layout and 16-byte alignment already fit; anything else is copied.  Returns the (reference) names shared."""
+        if self._fused is not None:
+            back = {}
+            mapped = []
+            for name, t in named_tensors:
+                m = self._to_fused_name(name.replace("speculator.", ""))
+                if m is not None:
+                    back[m] = name
+                    mapped.append((m, t))
+            return [back[m] for m in self._fused.share_parameters(mapped)]
+        shared, rest = [], []
+        for name, t in named_tensors:
+            name = name.replace("speculator.", "")
+            if name.startswith("qhead") or name not in self._params:
+                continue
+            p = self._params[name]
+            if (tuple(t.shape) == tuple(p.shape) and t.dtype == self.dtype and t.device == p.device
+                    and t.is_contiguous() and t.data_ptr() % 16 == 0):
+                self._params[name] = t.detach()
+                shared.append(name)
+            else:
+                rest.append((name, t))
+        self.cuda_graphs.clear()
+        if rest:
+            self.load_weights(rest)
+        return shared
+
     def _idx(self, head_index: int, proj: bool = False) -> int:
         if not self.tie_weights:
             return head_index

@@ -154,3 +154,37 @@ def test_against_the_unmodified_reference_class_on_cuda():
             total += exp.numel()
     print(f"sum_rnn multi-stage, unmodified reference class on CUDA vs ours: {agree}/{total}")
     assert agree / total >= 0.999
+
+
+@pytest.mark.parametrize("emb,proj,inner", [("512.512", "512.512", "512.1024"), ("512", "512", "512")])
+def test_one_call_drop_in_routes_sum_rnn(emb, proj, inner):
+    """integration.patch_lstm_speculator(): the unmodified reference class with method = "sum_rnn" (stacked or single
+    dims) answers through the native twin, which shares the module's parameter storage."""
+    from oracle import ref_class
+    if ref_class.reference_root() is None:
+        pytest.skip("reference sources not shipped (baseline/_ref/arctic_inference missing)")
+    from arcticinference_b200 import integration
+    from oracle.gen_golden_sumrnn import build_reference
+    spec = ref_class.load_reference_module()
+    cls = spec.ArcticLSTMSpeculator
+    V, H, S, B = 32000, 1024, 3, 24
+    w = R.make_sumrnn_weights(V, H, emb, proj, inner, S, True, torch.bfloat16, seed=0, device=DEV)
+    with torch.inference_mode():
+        ref = build_reference(spec, V, H, emb, proj, inner, S, True, B, torch.bfloat16, w, device=DEV)
+        ids, hid = O.make_inputs(B, V, H, torch.bfloat16, seed=21, device=DEV)
+        before = ref.generate_proposals(ids, hid, S).clone()
+        try:
+            integration.patch_lstm_speculator(cls)
+            after = ref.generate_proposals(ids, hid, S)
+            twin = ref._b200_impl
+            assert type(twin).__name__ == "ArcticSumRNNSpeculator"
+            mine = dict(twin.named_parameters())
+            shared = [k for k, p in ref.named_parameters() if mine[k].data_ptr() == p.data_ptr()]
+            assert "head.0.weight" in shared and "emb.0.0.weight" in shared and "proj.0.0.weight" in shared
+            assert torch.equal(after, twin.generate_proposals(ids, hid, S))
+            assert (after == before).float().mean().item() >= 0.999
+            with pytest.raises(ValueError, match="Max speculative tokens"):
+                ref.generate_proposals(ids, hid, S + 1)
+        finally:
+            integration.unpatch_lstm_speculator(cls)
+        assert torch.equal(ref.generate_proposals(ids, hid, S), before)
