@@ -100,6 +100,12 @@ if what in ("pair",):
         rows.append(run_case(M, N, K, False, warm_x=True, **DEFAULTS))
         for bn in (96, 128, 192, 256):
             rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "gate_block_n": bn}))
+if what in ("single",):
+    # 129..512 rows: CTA pairs (default) vs the single-CTA kernel with 2 m-tiles (gemm_2cta = 0), gate shapes
+    for (M, N, K) in ((256, 11520, 2880), (512, 11520, 2880), (256, 16384, 4096), (512, 16384, 4096), (200, 11520, 2880)):
+        for two in (1, 0):
+            rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "gemm_2cta": two}))
+    tune(gemm_2cta=1)
 if what in ("bound",):
     # what bounds the CTA-pair kernel: the same launches with the x loads (1), the W loads (2) or both (3) left out
     # after the first ring fill (debug flavour only; results are garbage, the timing is the point)
