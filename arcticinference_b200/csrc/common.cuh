@@ -71,6 +71,8 @@ struct Tune {
   int max_stages = 0;      // debug: cap the smem ring depth (0 = as many as fit)
   int gate_kbs = 2;        // k-blocks per TMA request / pipeline stage of the store-epilogue GEMM (1 or 2)
   int head_kbs = 2;        // ... of the arg-max (vocab head) GEMM (applies to <= 64 rows only)
+  int pair_gate_kbs = 0;   // CTA-pair kernel (129..512 rows): k-blocks per TMA request, store-epilogue GEMM (0 = auto, 1..4)
+  int pair_head_kbs = 0;   // the same for the arg-max head
 };
 #ifdef AB200_DEBUG
 Tune& tune_mut();

@@ -275,21 +275,25 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
   const int kbs = MT == 1 ? p.kbs : 1;
   const uint32_t b_pitch = b_bytes / kbs;     // bytes of one k-block slab of W
   auto n0_of = [&](int g) { return (static_cast<int>(blockIdx.x) + (g / num_kb) * static_cast<int>(gridDim.x)) * p.block_n; };
-  auto load_x = [&](int g, int stage) {
+  // (kb = pipeline step inside the tile, n0 = first weight row of the tile: the steady-state loop keeps them as
+  //  running counters - no division by run-time values on the producer's per-step path)
+  auto load_x_at = [&](int kb, int stage) {
     const uint32_t sa = smem_base + stage * stage_bytes;
     if (kbs == 2) {
-      tma_load_3d(sa, &tmap_x, full_bar(stage), 0, 0, 2 * (g % num_kb), kEvictLast);
+      tma_load_3d(sa, &tmap_x, full_bar(stage), 0, 0, 2 * kb, kEvictLast);
     } else {
 #pragma unroll
       for (int t = 0; t < MT; ++t)
-        tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), (g % num_kb) * kKElems, t * kTileM, kEvictLast);
+        tma_load_2d(sa + t * kABytes, &tmap_x, full_bar(stage), kb * kKElems, t * kTileM, kEvictLast);
     }
   };
-  auto load_w = [&](int g, int stage) {
+  auto load_w_at = [&](int kb, int n0, int stage) {
     const uint32_t sa = smem_base + stage * stage_bytes;
-    if (kbs == 2) tma_load_3d(sa + kASlot, &tmap_w, full_bar(stage), 0, n0_of(g), 2 * (g % num_kb), kEvictFirst);
-    else tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), (g % num_kb) * kKElems, n0_of(g), kEvictFirst);
+    if (kbs == 2) tma_load_3d(sa + kASlot, &tmap_w, full_bar(stage), 0, n0, 2 * kb, kEvictFirst);
+    else tma_load_2d(sa + kASlot, &tmap_w, full_bar(stage), kb * kKElems, n0, kEvictFirst);
   };
+  auto load_x = [&](int g, int stage) { load_x_at(g % num_kb, stage); };
+  auto load_w = [&](int g, int stage) { load_w_at(g % num_kb, n0_of(g), stage); };
   const int pre = total < p.pre_stages ? total : p.pre_stages;
 
   if (warp == 0 && lane == 0) {
@@ -346,11 +350,15 @@ gemm_tn_sm100(const __grid_constant__ CUtensorMap tmap_x,
       for (int g = 0; g < pre; ++g) load_x(g, g);
       int stage = pre == stages ? 0 : pre;
       uint32_t phase = pre == stages ? 1u : 0u;
+      int kb = pre % num_kb;
+      int n0 = n0_of(pre);
+      const int n0_step = static_cast<int>(gridDim.x) * p.block_n;
       for (int g = pre; g < total; ++g) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-        load_x(g, stage);
-        load_w(g, stage);
+        load_x_at(kb, stage);
+        load_w_at(kb, n0, stage);
+        if (++kb == num_kb) { kb = 0; n0 += n0_step; }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
       if (p.late_trigger) pdl_launch_dependents();
@@ -587,6 +595,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* desc, 
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
+                                                int32_t c1, int32_t c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 // the same load, delivered to the same shared-memory offset of every CTA in `mask` (cluster ranks); the bytes are
 // counted on the stage barrier of EACH destination's pair leader (peer bit cleared in every destination)
 __device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const void* desc, uint32_t bar, int32_t c0,
@@ -644,8 +660,13 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap& tmap_x, const 
   auto tile_of = [&](int round) { return CL == 4 ? 2 * (pair + round * npairs) + sub : pair + round * npairs; };
   const int stages = p.stages;
   const int half_n = p.block_n >> 1;
-  const uint32_t b_bytes = static_cast<uint32_t>(half_n) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  // kbs > 1: a stage holds kbs k-blocks per operand, fetched by ONE 3-D request each ([A kb0 | A kb1 ..][B kb0 | B kb1 ..]):
+  // half the TMA requests and barrier round trips per byte, as in the single-CTA kernel (profiles/r2_gemm_tune.md s.2, s.8)
+  const int kbs = CL == 4 ? 1 : p.kbs;
+  const uint32_t b_pitch = static_cast<uint32_t>(half_n) * 128u;   // one k-block slab of this CTA's half of the W tile
+  const uint32_t a_bytes = kABytes * static_cast<uint32_t>(kbs);
+  const uint32_t b_bytes = b_pitch * static_cast<uint32_t>(kbs);
+  const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                      // used in the leader only
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };          // one per CTA
@@ -698,47 +719,65 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap& tmap_x, const 
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       const int total = my_items * num_kb;
-      auto n0_of = [&](int g) { return tile_of((g / num_kb) / MH) * p.block_n + static_cast<int>(rank) * half_n; };
-      auto load_x = [&](int g, int stage) {
-        const int row0 = ((g / num_kb) % MH) * 2 * kTileM + static_cast<int>(rank) * kTileM;
-        if constexpr (CL == 4) {
-          // rows [sub*64, sub*64 + 64) of this CTA's 128, to both CTAs of the cluster with this pair rank
-          tma_load_2d_2sm_mc(smem_base + stage * stage_bytes + sub * (kABytes / 2), &tmap_x, full_bar(stage),
-                             (g % num_kb) * kBlockK, row0 + sub * (kTileM / 2),
-                             static_cast<uint16_t>((1u << rank) | (4u << rank)), kEvictLast);
-        } else {
-          tma_load_2d_2sm(smem_base + stage * stage_bytes, &tmap_x, full_bar(stage), (g % num_kb) * kBlockK, row0,
-                          kEvictLast);
+      // Position in this CTA's (tile, m-block, k-step) sequence as running counters: the producer thread's per-step
+      // instruction path is on the critical path of the pair kernel (a handful of extra instructions per step cost
+      // the debug flavour 15 %), so no division / modulo by run-time values in here.
+      struct Cursor { int kb, mhi, round; };
+      auto advance = [&](Cursor& c) {
+        if (++c.kb == num_kb) {
+          c.kb = 0;
+          if (++c.mhi == MH) { c.mhi = 0; ++c.round; }
         }
       };
-      auto load_w = [&](int g, int stage) {
-        tma_load_2d_2sm(smem_base + stage * stage_bytes + kABytes, &tmap_w, full_bar(stage), (g % num_kb) * kBlockK,
-                        n0_of(g), kEvictFirst);
+      auto load_x = [&](const Cursor& c, int stage) {
+        const int row0 = c.mhi * 2 * kTileM + static_cast<int>(rank) * kTileM;
+        const uint32_t dst = smem_base + stage * stage_bytes;
+        if constexpr (CL == 4) {
+          // rows [sub*64, sub*64 + 64) of this CTA's 128, to both CTAs of the cluster with this pair rank
+          tma_load_2d_2sm_mc(dst + sub * (kABytes / 2), &tmap_x, full_bar(stage), c.kb * kBlockK,
+                             row0 + sub * (kTileM / 2), static_cast<uint16_t>((1u << rank) | (4u << rank)), kEvictLast);
+        } else if (kbs > 1) {
+          tma_load_3d_2sm(dst, &tmap_x, full_bar(stage), 0, row0, kbs * c.kb, kEvictLast);
+        } else {
+          tma_load_2d_2sm(dst, &tmap_x, full_bar(stage), c.kb * kBlockK, row0, kEvictLast);
+        }
+      };
+      auto load_w = [&](const Cursor& c, int stage) {
+        const int n0 = tile_of(c.round) * p.block_n + static_cast<int>(rank) * half_n;
+        const uint32_t dst = smem_base + stage * stage_bytes + a_bytes;
+        if (kbs > 1) tma_load_3d_2sm(dst, &tmap_w, full_bar(stage), 0, n0, kbs * c.kb, kEvictFirst);
+        else tma_load_2d_2sm(dst, &tmap_w, full_bar(stage), c.kb * kBlockK, n0, kEvictFirst);
       };
       const int pre = total < p.pre_stages ? total : p.pre_stages;
+      Cursor cw{0, 0, 0}, cx{0, 0, 0};
       for (int g = 0; g < pre; ++g) {
         if (rank == 0) mbar_arrive_expect_tx(full_bar(g), p.tx_bytes);
-        load_w(g, g);
+        load_w(cw, g);
+        advance(cw);
       }
       pdl_wait();
       trace_stamp(p.trace, 1);
-      for (int g = 0; g < pre; ++g) load_x(g, g);
+      for (int g = 0; g < pre; ++g) {
+        load_x(cx, g);
+        advance(cx);
+      }
       int stage = pre == stages ? 0 : pre;
       uint32_t phase = pre == stages ? 1u : 0u;
-      for (int g = pre; g < total; ++g) {
+      for (int g = pre; g < total; ++g) {       // cw == cx from here on
         mbar_wait(empty_bar(stage), phase ^ 1u);
 #ifdef AB200_DEBUG
         // bound-finding experiment (WRONG results, timing only): leave operand loads out after the first ring fill
         const uint32_t skip = static_cast<uint32_t>(p.dbg_skip);
-        const uint32_t tx = p.tx_bytes - ((skip & 1u) ? 2u * kABytes : 0u) - ((skip & 2u) ? 2u * b_bytes : 0u);
+        const uint32_t tx = p.tx_bytes - ((skip & 1u) ? 2u * a_bytes : 0u) - ((skip & 2u) ? 2u * b_bytes : 0u);
         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), tx);
-        if (!(skip & 1u)) load_x(g, stage);
-        if (!(skip & 2u)) load_w(g, stage);
+        if (!(skip & 1u)) load_x(cw, stage);
+        if (!(skip & 2u)) load_w(cw, stage);
 #else
         if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-        load_x(g, stage);
-        load_w(g, stage);
+        load_x(cw, stage);
+        load_w(cw, stage);
 #endif
+        advance(cw);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
       if (p.late_trigger) pdl_launch_dependents();
@@ -762,12 +801,14 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap& tmap_x, const 
           }
           if (elect_one()) {
             const uint32_t sa = smem_base + stage * stage_bytes;
-            const uint64_t da = smem_desc_sw128(sa);
-            const uint64_t db = smem_desc_sw128(sa + kABytes);
             const uint32_t tmem_d = tmem_base + acc * kAcc;
+            for (int kk = 0; kk < kbs; ++kk) {
+              const uint64_t da = smem_desc_sw128(sa + kk * kABytes);
+              const uint64_t db = smem_desc_sw128(sa + a_bytes + kk * b_pitch);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_2sm_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_2sm_bf16(tmem_d, da + 2u * k, db + 2u * k, p.idesc, (kb | kk | k) != 0 ? 1u : 0u);
+            }
             umma_commit_2sm(empty_bar(stage), CL == 4 ? 0xF : 0x3);
             if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc), static_cast<uint16_t>(0x3u << (2 * sub)));
           }
@@ -1186,21 +1227,30 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   const int forced_bn = EPI == EPI_STORE ? tune().gate_block_n : tune().head_block_n;   // debug sweeps only
   if (forced_bn >= 32 && forced_bn <= 256 && forced_bn % 32 == 0) bn = forced_bn;
   const int num_n_tiles = static_cast<int>((n_valid + bn - 1) / bn);
-  const uint32_t stage_bytes = kABytes + (bn / 2) * 128;
+  // two k-blocks per TMA request where it pays (tools/gemm_tune.py pairk, profiles/r2_gemm_tune.md s.8)
+  int kbs = 1;
+  int want_kbs = EPI == EPI_STORE ? tune().pair_gate_kbs : tune().pair_head_kbs;
+  // 0 = auto: two k-blocks per request only for narrow tiles (each CTA's W slab of a k-block < 12 KB), where the fixed
+  // cost per request still shows (GPT-OSS gate at 256 / 512 rows: -10 %); wide tiles are level or 3-4 % better with one
+  if (want_kbs == 0) want_kbs = bn < 192 ? 2 : 1;
+  if (!cl4 && want_kbs >= 2 && want_kbs <= 4 && K % kBlockK == 0 && K >= want_kbs * kBlockK) kbs = want_kbs;
+  while (kbs > 1 && (kSmemLimit - 1024 - 256) / ((kABytes + (bn / 2) * 128) * kbs) < 2) --kbs;   // keep >= 2 stages
+  const uint32_t stage_bytes = (kABytes + (bn / 2) * 128) * kbs;
   int stages = (kSmemLimit - 1024 - 256) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (tune().max_stages >= 2 && stages > tune().max_stages) stages = tune().max_stages;
   AB200_REQUIRE(stages >= 2, AB200_E_INVALID, "bf16 GEMM: not enough shared memory");
   CUtensorMap tmx, tmw;
-  rc = get_tmap(&tmx, x, m_rows, K, ldx, cl4 ? kTileM / 2 : kTileM, 2);
+  rc = get_tmap(&tmx, x, m_rows, K, ldx, cl4 ? kTileM / 2 : kTileM, 2, kbs);
   if (rc != AB200_OK) return rc;
-  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2);
+  rc = get_tmap(&tmw, w, w_rows, K, ldw, bn / 2, 2, kbs);
   if (rc != AB200_OK) return rc;
   GemmParams p;
   p.m_rows = static_cast<int32_t>(m_rows);
   p.n_valid = static_cast<int32_t>(n_valid);
   p.block_n = bn;
   p.num_n_tiles = num_n_tiles;
-  p.num_k_blocks = static_cast<int32_t>((K + kBlockK - 1) / kBlockK);
+  p.num_k_blocks = static_cast<int32_t>(((K + kBlockK - 1) / kBlockK + kbs - 1) / kbs);   // pipeline steps per tile
   p.stages = stages;
   p.l2_prefetch_kb = 0;
 #ifdef AB200_DEBUG
@@ -1210,10 +1260,10 @@ static int launch_gemm_pass_2cta(const void* x, const void* w, int64_t m_rows, i
   p.pre_stages = tune().pre_stages < 0 ? stages : tune().pre_stages;
   if (p.pre_stages > stages) p.pre_stages = stages;
   p.m64 = 0;
-  p.kbs = 1;
+  p.kbs = kbs;
   p.a_pitch = 0;
   p.mh = mh;
-  p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u);   // both CTAs
+  p.tx_bytes = 2u * (static_cast<uint32_t>(kABytes) + static_cast<uint32_t>(bn / 2) * 128u) * kbs;   // both CTAs
   // instruction descriptor: D = f32, A/B = bf16, K-major, N >> 3, M = 256 >> 4
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) | (16u << 24);
   p.x_scales = nullptr;

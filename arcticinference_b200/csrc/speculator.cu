@@ -143,7 +143,7 @@ extern "C" int32_t ab200_debug_set_tunable(const char* name, int32_t value) {
       {"rows_per_pass", &t.rows_per_pass}, {"late_trigger", &t.late_trigger},
       {"pre_stages", &t.pre_stages}, {"l2_prefetch_kb", &t.l2_prefetch_kb}, {"gate_l2_prefetch", &t.gate_l2_prefetch}, {"gemm_4cta", &t.gemm_4cta}, {"dbg_skip", &t.dbg_skip},
       {"gate_block_n", &t.gate_block_n}, {"head_block_n", &t.head_block_n},
-      {"max_stages", &t.max_stages}, {"gate_mh2", &t.gate_mh2}, {"gate_kbs", &t.gate_kbs}, {"head_kbs", &t.head_kbs}};
+      {"max_stages", &t.max_stages}, {"gate_mh2", &t.gate_mh2}, {"gate_kbs", &t.gate_kbs}, {"head_kbs", &t.head_kbs}, {"pair_gate_kbs", &t.pair_gate_kbs}, {"pair_head_kbs", &t.pair_head_kbs}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) {
       *e.p = value;

@@ -100,6 +100,28 @@ if what in ("pair",):
         rows.append(run_case(M, N, K, False, warm_x=True, **DEFAULTS))
         for bn in (96, 128, 192, 256):
             rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "gate_block_n": bn}))
+if what in ("pairk",):
+    # CTA-pair kernel with two k-blocks per request: tile width / stage count sweep, head and gate shapes
+    K2 = {**DEFAULTS, "pair_gate_kbs": 2, "pair_head_kbs": 2}
+    for (M, N, K, head) in ((256, 128256, 4096, True), (256, 201088, 2880, True), (200, 128256, 4096, True)):
+        rows.append(run_case(M, N, K, head, warm_x=True, **{**DEFAULTS, "pair_head_kbs": 1}))
+        for bn in (0, 160, 192, 224, 256):
+            rows.append(run_case(M, N, K, head, warm_x=True, **{**K2, "head_block_n": bn}))
+    for (M, N, K) in ((256, 16384, 4096), (512, 16384, 4096), (256, 11520, 2880), (512, 11520, 2880), (256, 32768, 8192)):
+        rows.append(run_case(M, N, K, False, warm_x=True, **{**DEFAULTS, "pair_gate_kbs": 1}))
+        for bn in (0, 128, 160, 192, 224, 256):
+            rows.append(run_case(M, N, K, False, warm_x=True, **{**K2, "gate_block_n": bn}))
+    tune(pair_gate_kbs=0, pair_head_kbs=0)
+if what in ("pairk3",):
+    for kbs in (2, 3, 4):
+        K2 = {**DEFAULTS, "pair_gate_kbs": kbs, "pair_head_kbs": kbs}
+        for (M, N, K, head) in ((256, 128256, 4096, True), (256, 201088, 2880, True), (256, 16384, 4096, False),
+                                (512, 16384, 4096, False), (256, 11520, 2880, False), (512, 11520, 2880, False)):
+            rows.append(run_case(M, N, K, head, warm_x=True, **K2))
+            if kbs == 3 and head:
+                for bn in (192, 224):
+                    rows.append(run_case(M, N, K, head, warm_x=True, **{**K2, "head_block_n": bn}))
+    tune(pair_gate_kbs=0, pair_head_kbs=0)
 if what in ("single",):
     # 129..512 rows: CTA pairs (default) vs the single-CTA kernel with 2 m-tiles (gemm_2cta = 0), gate shapes
     for (M, N, K) in ((256, 11520, 2880), (512, 11520, 2880), (256, 16384, 4096), (512, 16384, 4096), (200, 11520, 2880)):

@@ -1,6 +1,6 @@
 """Dev (GPU box): graph-replay time of the cfg2 draft loop for settings of the debug library's launch tunables
 (ab200_debug_set_tunable).  The speculator class is pointed at the DEBUG flavour for this run only.
-    python tools/graph_tune.py l2_prefetch_kb=0,2,4,8 [B=64]"""
+    python tools/graph_tune.py l2_prefetch_kb=0,2,4,8 [B=64] [cfg=cfg2|cfg3|cfg3w|cfg4]"""
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,14 +12,17 @@ from arcticinference_b200.speculator import ArcticLSTMSpeculator
 
 dev = torch.device("cuda:0")
 lib = _capi.debug_lib()
-sweeps, B = [], 64
+sweeps, B, cfg = [], 64, "cfg2"
 for a in sys.argv[1:]:
     k, v = a.split("=")
     if k == "B":
         B = int(v)
+    elif k == "cfg":
+        cfg = v
     else:
         sweeps.append((k, [int(x) for x in v.split(",")]))
-V, H, D, S = (bench.CFG[k] for k in "VHDS")
+V, H, D, S = {"cfg2": tuple(bench.CFG[k] for k in "VHDS"), "cfg3": (128256, 8192, 4096, 4),
+              "cfg3w": (128256, 8192, 8192, 4), "cfg4": (201088, 2880, 2880, 3)}[cfg]
 model = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=dev)
 bench.synthetic_weights(model, 0)
 g = torch.Generator(device="cpu").manual_seed(1)
