@@ -647,10 +647,9 @@ def bench_cfg3_70b(dev, world, rank, steps, warmup, peak):
         del model
         torch.cuda.empty_cache()
     out["limiting_term"] = ("per-GPU time = weight stream (the whole head + gate matrices once per step, whatever "
-                            "the batch) while rows/GPU <= ~128; above that the pair GEMM, which at 256 rows is bound by L2 "
-                            "throughput (fills + W reads + re-reads of the activation tile = 3.1 GB per head launch; "
-                            "1.16-1.36 PFLOP/s against 1.85 with the loads left out, profiles/r2_gemm_tune.md s.6), "
-                            "reported here against the tensor roofline.  Splitting a FIXED batch "
+                            "the batch) while rows/GPU <= ~128; above that the pair GEMM, which at 256 rows runs within "
+                            "14 % of its own MMA + epilogue time (1.45 PFLOP/s while streaming at the power-capped "
+                            "clock, profiles/r2_gemm_tune.md s.8).  Splitting a FIXED batch "
                             "over more GPUs therefore shortens a proposal only from 256 -> 128 rows; below, every "
                             "GPU still streams all the weights, so the global tok/s stays flat (replicas pay off "
                             "with their own batches: the weak-scaling headline)")
