@@ -644,6 +644,15 @@ def bench_cfg3_70b(dev, world, rank, steps, warmup, peak):
         out[f"D{D}"] = {"ms_per_proposal": per, "value": units / max_ms * 1e3, "unit": UNIT,
                         "head": "FP8 qhead (padded batch <= 32: the reference's rule)" if model.uses_fp8_head(B) else "bf16",
                         "algorithmic_bytes_per_gpu": nbytes, **roofline_of(B, nbytes, flops, per, peak)}
+        if rank == 0 and D == CFG3["D_list"][0] and not model.uses_fp8_head(B):
+            # the reference's own torch path (cuBLAS + ATen, one CUDA graph) at THIS configuration's per-GPU batch
+            try:
+                model.qhead = None
+                tb = bench_gpu_torch_baseline(dev, model, max(5, min(steps, 20)), shape=(V, H, D, S, B))
+                tb["our_speedup"] = tb["ms_per_proposal"] / (ms / steps)
+                out[f"D{D}"]["gpu_torch_baseline"] = tb
+            except Exception as e:  # noqa: BLE001
+                out[f"D{D}"]["gpu_torch_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         del model
         torch.cuda.empty_cache()
     out["limiting_term"] = ("per-GPU time = weight stream (the whole head + gate matrices once per step, whatever "
@@ -678,6 +687,14 @@ def bench_cfg4_gptoss(dev, world, rank, steps, warmup, peak):
                           "head": "FP8 qhead (padded batch <= 32: the reference's rule)" if fp8_rule else "bf16",
                           "algorithmic_bytes_per_gpu": nbytes,
                           **roofline_of(B, nbytes, 2 * B * (4 * D * H + (S - 1) * 4 * D * D + S * D * V), per, peak)}}
+    if rank == 0 and not fp8_rule:
+        try:
+            model.qhead = None
+            tb = bench_gpu_torch_baseline(dev, model, max(5, min(steps, 20)), shape=(V, H, D, S, B))
+            tb["our_speedup"] = tb["ms_per_proposal"] / (ms / steps)
+            out["speculator"]["gpu_torch_baseline"] = tb
+        except Exception as e:  # noqa: BLE001
+            out["speculator"]["gpu_torch_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     del model
     torch.cuda.empty_cache()
     # KV write, cfg5 geometry
@@ -713,13 +730,14 @@ def bench_cfg4_gptoss(dev, world, rank, steps, warmup, peak):
     return out
 
 
-def bench_gpu_torch_baseline(dev, model, steps):
+def bench_gpu_torch_baseline(dev, model, steps, shape=None):
     """What the reference deploys on a GPU (arctic_speculator.py:805-842): its own eager torch path (cuBLAS GEMMs +
     ~35 ATen kernels per step) captured in ONE CUDA graph and replayed.  Uses the UNMODIFIED reference class when
-    its sources travelled (baseline/_ref), else the op-for-op port; same weights, same batch as the headline."""
+    its sources travelled (baseline/_ref), else the op-for-op port; same weights, same batch as `model` runs
+    (`shape` = (V, H, D, S, B); default: the headline configuration)."""
     import torch
     from oracle import speculator_ref as O
-    V, H, D, S, B = (CFG[k] for k in "VHDSB")
+    V, H, D, S, B = shape or tuple(CFG[k] for k in "VHDSB")
     weights = dict(model.named_parameters())
     kind = "port (oracle/speculator_ref.py, identical ATen ops)"
     ref = None
@@ -773,7 +791,7 @@ def bench_gpu_torch_baseline(dev, model, steps):
         graph_ms = e0.elapsed_time(e1) / steps
         ref_tokens = torch.cat(outs, -1)
         ours = model.generate_proposals(ids, hid, S)
-    res = {"what": "reference torch path on this GPU: cuBLAS + ATen kernels, whole 3-step loop in ONE CUDA graph "
+    res = {"what": f"reference torch path on this GPU: cuBLAS + ATen kernels, whole {S}-step loop in ONE CUDA graph "
                    "(arctic_speculator.py:805-842)", "kind": kind, "ms_per_proposal": graph_ms,
            "value": B * S / graph_ms * 1e3, "unit": UNIT, "eager_ms_per_proposal": eager_ms,
            "token_agreement_ours_vs_it": (ours == ref_tokens).float().mean().item()}
