@@ -1,5 +1,7 @@
 """Host-side mirror of the reference's ``ArcticMLPSpeculator`` - also the
-``method="sum_rnn"`` configuration of ``ArcticLSTMSpeculator`` with single-stage dims.
+``method="sum_rnn"`` configuration of ``ArcticLSTMSpeculator`` with single-stage dims (that class's parameter names
+``emb.i.0.weight`` ... and its stacked / list-valued dims are handled by ``sum_rnn_speculator.ArcticSumRNNSpeculator``,
+which delegates to this class when every stack has one stage).
 
 Reference: ``arctic_inference/vllm/spec_dec/arctic_speculator.py::ArcticMLPSpeculator``
 (:102-401): ``generate_states(last_tokens[B,1], previous_hidden_states[B,1,K], head_index)``
