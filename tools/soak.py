@@ -13,7 +13,7 @@ seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
 dev = torch.device("cuda:0")
 V, H, D, S = (bench.CFG[k] for k in "VHDS")
 total_bad = 0
-for B, kw in ((64, {}), (33, {}), (8, {}), (200, {}), (64, {"fp8_head_max_batch": 1 << 30})):
+for B, kw in ((64, {}), (33, {}), (8, {}), (200, {}), (300, {}), (512, {}), (64, {"fp8_head_max_batch": 1 << 30})):
     model = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=dev, **kw)
     bench.synthetic_weights(model, 0)
     eager = ArcticLSTMSpeculator(vocab_size=V, input_hidden_dim=H, inner_dim=D, n_predict=S, max_num_seqs=B, device=dev,
